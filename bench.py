@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the per-pixel SVBRDF optimisation hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's torch-CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...          # material-sharded, one material per rank
+
+A step is one pass of the hot path over one material: clamp -> render (N lights) -> L2 -> backward
+-> Adam (the loop body of SvbrdfOptim.optim, /root/reference/src/svbrdf.py:60-71) at the
+configuration BASELINE.json quotes the metric on: 1024 x 1024 texels, 9 co-located flash lights,
+fp32 targets, synthetic random SVBRDF maps (`optim_perpixel` uses the L2 loss only).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline`, `cpu_baseline`,
+`e2e` (per-step host->device upload of the step's targets + device->host loss read, through the
+public SvbrdfOptim API), `e2e_job` (one optim() call of 20 epochs incl. uploads/downloads),
+`clocks`, `gpu_launches`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("SVBRDF_B200_QUIET", "1")
+
+import torch as th  # noqa: E402
+
+RES, LIGHTS = 1024, 9
+LR = 0.01
+JOB_EPOCHS = 20               # run.py:55-56: the refinement recipe runs 20 epochs per optim_perpixel call
+N_MATERIALS_CYCLED = 4        # inputs cycled so that every step streams cold data (4 x 340 MB >> 126 MB L2)
+METRIC = "pixel_light_samples_per_s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--res", type=int, default=RES)
+    ap.add_argument("--lights", type=int, default=LIGHTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, extra=None):
+    cfg = {
+        "workload": f"optim_perpixel fused step (clamp+render+L2+backward+Adam), {args.res}x{args.res} texels, "
+                    f"{args.lights} co-located flash lights, fp32 targets (BASELINE.json configs[1])",
+        "res": args.res, "lights": args.lights, "lr": LR, "target_dtype": "f32",
+        "samples_per_step_per_gpu": args.res * args.res * args.lights,
+        "l2": f"inputs larger than L2: {N_MATERIALS_CYCLED} materials x "
+              f"{(216 + 12 * args.lights) * args.res * args.res / 1e6:.0f} MB cycled, no reuse between consecutive steps",
+        "sharding": "material-sharded: one independent material per GPU, no data-path collective",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(res, lights, steps, warmup, budget_s=150.0):
+    """Times the reference's torch-CPU path (oracle/torch_port.py, op-for-op the reference's
+    Microfacet.eval + MSELoss + backward + torch.optim.Adam.step) on all host cores.  Each step
+    is a bounded sample of the workload: a band of `rows` full-width rows, all lights, sized after
+    a probe so the whole run fits `budget_s`."""
+    from oracle import torch_port as tp
+    from svbrdf_diff_renderer_b200 import synth
+
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    cl = synth.calibration(lights)
+    gt, t0 = synth.random_textures(res, 1), synth.random_textures(res, 2)
+
+    def make(rows):
+        band = (0, rows)
+        sc = tp.Scene(res, cl[0], cl[1], cl[2], synth.IM_SIZE_CM, th.float32, band)
+        with th.no_grad():
+            tgt = tp.shade(sc, gt[:, :, :rows])
+        tex = t0[:, :, :rows].clone().requires_grad_(True)
+        opt = th.optim.Adam([tex], lr=LR, betas=(0.9, 0.999))
+        return sc, tgt, tex, opt
+
+    def step(sc, tgt, tex, opt):
+        loss = tp.l2_loss(tp.shade(sc, tex.clamp(-1, 1)), tgt)     # svbrdf.py:60-63
+        opt.zero_grad()
+        loss.backward()
+        opt.step()                                                  # svbrdf.py:69-71
+        return loss
+
+    probe_rows = min(res, 64)
+    state = make(probe_rows)
+    step(*state)
+    t = time.perf_counter()
+    step(*state)
+    per_row = (time.perf_counter() - t) / probe_rows
+    rows = int(max(min(res, budget_s / max(steps + warmup, 1) / per_row), min(res, 32)))
+    state = make(rows)
+    for _ in range(warmup):
+        step(*state)
+    t = time.perf_counter()
+    for _ in range(steps):
+        step(*state)
+    dt = time.perf_counter() - t
+    samples = rows * res * lights
+    return {"value": samples * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} optim steps (after {warmup} warm-up) on a {rows}-row x {res}-col band of the {res}x{res}x{lights} workload, "
+                      f"torch {th.__version__} CPU fp32, {cores} threads",
+            "ms_per_step_sample": dt / steps * 1e3, "iters_per_s_full_image": (samples * steps / dt) / (res * res * lights)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_run(args.res, args.lights, args.steps, max(args.warmup, 1))
+    v = base["value"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": args.res * args.res * args.lights / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, {"reference_path": "oracle/torch_port.py (op-for-op restatement of the reference's torch path; "
+                                                       "the reference itself is pure Python and does not travel to the GPU box)"}),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import ctypes
+
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import _native as nv
+    from svbrdf_diff_renderer_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not th.cuda.is_available():
+        raise RuntimeError("bench.py --impl b200 needs a GPU (the CUDA path has no CPU fallback)")
+    th.cuda.set_device(local)
+    dev = th.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    res, n, K, W = args.res, args.lights, args.steps, max(args.warmup, 3)
+    P = res * res
+    L = nv.lib()
+
+    # ---- synthetic inputs (CPU-seeded); every rank gets its own materials ----
+    cl = [c.to(dev) for c in synth.calibration(n)]
+    r = pkg.Microfacet(res, n, synth.IM_SIZE_CM, cl, dev)
+    mats = []
+    for i in range(N_MATERIALS_CYCLED):
+        seed = 1000 + 2 * (rank * N_MATERIALS_CYCLED + i)
+        with th.no_grad():
+            tgt = r.eval(synth.random_textures(res, seed).to(dev)).contiguous()
+        tex0 = synth.random_textures(res, seed + 1).to(dev)
+        mats.append({"target": tgt, "tex0": tex0, "tex": tex0[0].clone(), "m": th.zeros(9, res, res, device=dev),
+                     "v": th.zeros(9, res, res, device=dev)})
+    ws = r._workspace()
+    geom = r._geom(r._pow)
+    loss_dev = th.zeros(1, device=dev)
+    stream = nv.stream_ptr(dev)
+    step_no = [0]
+
+    def fused_step(mat, with_loss=True):
+        step_no[0] += 1
+        a = nv.Adam(LR, 0.9, 0.999, 1e-8, step_no[0])
+        nv.check(L.svbrdf_l2_adam_step(ctypes.byref(geom), nv.ptr(mat["tex"]), nv.ptr(mat["m"]), nv.ptr(mat["v"]), nv.ptr(mat["target"]), 0,
+                                       ctypes.byref(a), nv.ptr(loss_dev) if with_loss else None, None, nv.ptr(ws), stream), "l2_adam_step")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = th.tensor([ms], device=dev, dtype=th.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: device-resident inputs, K fused steps (main kernel + loss finalize) ----
+    for i in range(W):
+        fused_step(mats[i % N_MATERIALS_CYCLED])
+    with ClockSampler(local) as clk:
+        ms = timed(lambda i: fused_step(mats[i % N_MATERIALS_CYCLED]), K)
+    samples_per_step = P * n
+    value = samples_per_step * world * K / (ms * 1e-3)
+
+    # ---- roofline: the dominant kernel alone (no loss finalize), same cycling ----
+    for i in range(3):
+        fused_step(mats[i % N_MATERIALS_CYCLED], with_loss=False)
+    ms_k = timed(lambda i: fused_step(mats[i % N_MATERIALS_CYCLED], with_loss=False), K) / K
+    algo_bytes = (216 + 12 * n) * P
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(f"l2_adam_{res}x{n}")
+    except Exception:
+        pass
+    achieved = algo_bytes / (ms_k * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "svbrdf::texel_kernel<kModeL2Adam> (fused render+L2+backward+Adam)", "kernel_ms": ms_k,
+                "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_texel": 216 + 12 * n, "peak_source": peak_src,
+                "samples_per_s_kernel_only": samples_per_step / (ms_k * 1e-3)}
+
+    # ---- e2e: per step, upload that step's targets from pinned host memory, run, read the loss back ----
+    e2e = e2e_job = None
+    if not args.no_e2e:
+        o = pkg.SvbrdfOptim(dev, r)
+        host_targets = [m["target"].cpu().pin_memory() for m in mats[:2]]
+        stage = th.empty_like(mats[0]["target"])
+        o.init_from_tex(mats[0]["tex0"].clone())
+        o.load_targets(stage)
+        host_loss = th.empty(1, dtype=th.float32).pin_memory()
+        e2e_steps = max(3, min(K, 20))
+        em, ev = th.zeros(9, res, res, device=dev), th.zeros(9, res, res, device=dev)
+
+        def e2e_step(i):
+            stage.copy_(host_targets[i % 2], non_blocking=True)                     # H2D of this step's inputs
+            a = nv.Adam(LR, 0.9, 0.999, 1e-8, i + 1)
+            nv.check(L.svbrdf_l2_adam_step(ctypes.byref(geom), nv.ptr(o.textures.data), nv.ptr(em), nv.ptr(ev), nv.ptr(stage), 0,
+                                           ctypes.byref(a), nv.ptr(loss_dev), None, nv.ptr(ws), stream), "l2_adam_step")
+            host_loss.copy_(loss_dev, non_blocking=True)                            # D2H of the step's result
+            th.cuda.current_stream().synchronize()
+
+        for i in range(2):
+            e2e_step(i)
+        ms_e = timed(e2e_step, e2e_steps)
+        e2e = {"value": samples_per_step * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": stage.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
+               "what": "every step re-uploads its [N,3,R,R] fp32 targets from pinned host memory, runs the fused step, reads the loss back"}
+
+        # the call a user makes: SvbrdfOptim.optim(20 epochs) on host-resident inputs, result back on the host
+        host_tex0 = mats[0]["tex0"].cpu().pin_memory()
+        host_out = th.empty_like(host_tex0).pin_memory()
+
+        def job(i):
+            o.load_targets(host_targets[i % 2].to(dev, non_blocking=True))
+            o.init_from_tex(host_tex0.to(dev, non_blocking=True))
+            losses = o.optim(JOB_EPOCHS, LR, None, False, progress=False)          # includes the loss-curve readback
+            host_out.copy_(o.textures.detach(), non_blocking=True)
+            th.cuda.current_stream().synchronize()
+            return losses
+
+        job(0)
+        jobs = 3
+        ms_j = timed(job, jobs)
+        e2e_job = {"value": samples_per_step * world * JOB_EPOCHS * jobs / (ms_j * 1e-3), "unit": UNIT, "epochs_per_call": JOB_EPOCHS,
+                   "ms_per_call": ms_j / jobs, "h2d_bytes_per_call": stage.numel() * 4 + host_tex0.numel() * 4,
+                   "d2h_bytes_per_call": host_out.numel() * 4 + 4 * JOB_EPOCHS,
+                   "what": "SvbrdfOptim.optim(20 epochs): pinned-host targets + init maps uploaded, 20 fused epochs, maps + loss curve downloaded"}
+
+    # ---- cpu baseline (rank 0 only, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = cpu_reference_run(res, n, 3, 1, budget_s=25.0)
+        cpu = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "clocks": clk.summary(),
+            "gpu_launches": 2 * K, "gpu_launches_what": "per step: texel_kernel<L2Adam> + finalize_kernel (loss reduction)",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

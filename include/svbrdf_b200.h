@@ -1,0 +1,115 @@
+/* svbrdf_b200 — C ABI of the B200-native per-pixel SVBRDF optimisation path.
+ *
+ * The reference (tflsguoyu/svbrdf-diff-renderer) is pure Python and exposes no FFI; its
+ * boundary for this path is the Python API of src/microfacet.py, src/svbrdf.py and
+ * src/scripts.py::optim_perpixel.  This header is the native boundary a replacement binds
+ * instead of the torch-eager op sequence; every entry point names the reference interface it
+ * stands in for.  The Python classes in svbrdf_diff_renderer_b200/ bind it with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous memory owned by the caller, except
+ *    `const svbrdf_geom_t*`, which is a host struct read during the call;
+ *  - images are planar: textures [9, rows, res] (channel order of svbrdf.py:38: diffuse 0:3,
+ *    normal-xy 3:5, roughness 5, specular 6:9), image stacks [N, 3, rows, res];
+ *    `plane_stride` (elements) is the distance between consecutive planes;
+ *  - calls enqueue work on `stream` and return; they never allocate, free or synchronise;
+ *  - return value: 0 on success, a positive cudaError_t, or a negative SVBRDF_E_* code;
+ *    svbrdf_error_string() maps either to text;  no exceptions cross the boundary;
+ *  - re-entrant: no global mutable state; concurrent calls on different streams/devices are
+ *    safe as long as they use different workspaces.
+ */
+#ifndef SVBRDF_B200_H_
+#define SVBRDF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVBRDF_B200_ABI_VERSION 1
+
+typedef struct CUstream_st* svbrdf_stream_t; /* == cudaStream_t */
+
+enum {
+  SVBRDF_E_BADARG = -1,    /* null pointer, non-positive size, misaligned pointer */
+  SVBRDF_E_UNSUPPORTED = -2 /* unknown target dtype / too many lights for shared memory */
+};
+
+/* dtype of the target image stack handed to the L2 entry points */
+enum {
+  SVBRDF_TARGET_F32 = 0, /* what SvbrdfIO.load_images_th returns (svbrdf.py:191-204) */
+  SVBRDF_TARGET_U8 = 1   /* the PNG bytes themselves; decoded as float(b)/255 in-kernel (imageio.py:18-19) */
+};
+
+/* Capture geometry: the arguments of Microfacet.__init__ (microfacet.py:10-26). */
+typedef struct svbrdf_geom_t {
+  const float* camera_pos; /* [n_lights,3]  cl[0] */
+  const float* light_pos;  /* [n_lights,3]  cl[1] */
+  const float* light_pow;  /* [3]           cl[2]; read at kernel time, so update_light() is a pointer swap */
+  float size;              /* im_size in cm (microfacet.py:17) */
+  int32_t res;             /* full image resolution (square, microfacet.py:85-86) */
+  int32_t rows;            /* rows held by the buffers of this call (== res, or a row band) */
+  int32_t row_offset;      /* global row index of buffer row 0 */
+  int32_t n_lights;        /* N of this call (a light shard in view-sharded runs) */
+  int64_t plane_stride;    /* elements between planes; 0 means rows*res */
+} svbrdf_geom_t;
+
+/* Adam hyper-parameters of torch.optim.Adam as SvbrdfOptim.optim builds it (svbrdf.py:50,52):
+ * amsgrad off, weight decay 0.  `step` is 1-based (the value torch's state['step'] has after
+ * its increment). */
+typedef struct svbrdf_adam_t {
+  double lr, beta1, beta2, eps;
+  int64_t step;
+} svbrdf_adam_t;
+
+int svbrdf_abi_version(void);
+const char* svbrdf_error_string(int code);
+
+/* Bytes of scratch (per concurrent call) the entry points below need for block partials. */
+size_t svbrdf_workspace_bytes(int32_t res, int32_t rows);
+
+/* Microfacet.eval forward (microfacet.py:84-120):  tex [9,rows,res] -> out [N,3,rows,res]. */
+int svbrdf_render_fwd(const svbrdf_geom_t* geom, const float* tex, float* out, svbrdf_stream_t stream);
+
+/* Vector-Jacobian product of Microfacet.eval (what loss.backward() runs through the autograd
+ * graph of microfacet.py:84-120): grad_out [N,3,rows,res] -> grad_tex [9,rows,res], and, when
+ * grad_pow != NULL, d/d light_pow [3] (the update_light path, microfacet.py:81-82).
+ * Recomputes the forward; nothing image-sized is saved between fwd and bwd. */
+int svbrdf_render_bwd(const svbrdf_geom_t* geom, const float* tex, const float* grad_out, float* grad_tex,
+                      float* grad_pow, void* workspace, svbrdf_stream_t stream);
+
+/* clamp(-1,1) -> eval -> MSELoss -> backward (svbrdf.py:60-70) without the optimiser step.
+ * n_total is the light count of the WHOLE problem (the MSE mean divides by n_total*3*res*res);
+ * a view shard passes its own lights in geom and the global count here, so shard results add.
+ * loss_out[0] receives this call's share of the mean-squared error. */
+int svbrdf_l2_grad(const svbrdf_geom_t* geom, const float* tex, const void* target, int32_t target_dtype,
+                   int32_t n_total, float* grad_tex, float* loss_out, float* grad_pow, void* workspace,
+                   svbrdf_stream_t stream);
+
+/* One iteration of SvbrdfOptim.optim's loop body (svbrdf.py:60-71) in a single pass:
+ * clamp -> eval -> MSE -> backward -> Adam.step, updating tex/m/v [9,rows,res] in place.
+ * The rendered image is never materialised.  loss_out[0] receives the loss BEFORE the update
+ * (what svbrdf.py:64 logs).  When pow_state != NULL (optim_light=True, svbrdf.py:48-50) it
+ * points at float[6] = Adam m[3], v[3] of light_pow, and geom->light_pow is updated in place. */
+int svbrdf_l2_adam_step(const svbrdf_geom_t* geom, float* tex, float* m, float* v, const void* target,
+                        int32_t target_dtype, const svbrdf_adam_t* adam, float* loss_out, float* pow_state,
+                        void* workspace, svbrdf_stream_t stream);
+
+/* `epochs` iterations of the above, enqueued back to back; loss_curve[e] is epoch e's loss.
+ * adam->step is the step number of the first iteration. */
+int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v, const void* target,
+                       int32_t target_dtype, const svbrdf_adam_t* adam, int32_t epochs, float* loss_curve,
+                       float* pow_state, void* workspace, svbrdf_stream_t stream);
+
+/* torch.optim.Adam.step on a flat fp32 array (adam.py:531-547), used after the gradient
+ * all-reduce of a view-sharded run. */
+int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,
+                      svbrdf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVBRDF_B200_H_ */

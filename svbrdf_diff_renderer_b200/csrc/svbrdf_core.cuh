@@ -1,0 +1,424 @@
+// Per-texel arithmetic of the SVBRDF render / backward / Adam path.
+//
+// One texel is shaded under N point lights; everything a texel needs lives in
+// registers: a prologue turns the 9 texture channels into material parameters,
+// the light loop accumulates loss and parameter gradients, an epilogue chains
+// the gradients back to the 9 channels (and, in the fused mode, applies Adam).
+//
+// The math restates /root/reference/src/microfacet.py:64-120 (forward) and the
+// derivative torch autograd produces for it, plus torch.optim.Adam's update
+// (torch/optim/adam.py:531-547) — written from the formulas, not from the code:
+//   * the half vector is never materialised: with unit l, v
+//         |l+v|^2 = 2 + 2 l.v,  n.h = (n.l + n.v)/|l+v|,  v.h = (1 + l.v)/|l+v|
+//   * v and l are never materialised either: n.v = (n.V) * rsqrt(V.V)
+//   * x^2.2 is evaluated as x^2 * x^0.2 so the lg2/ex2 error is scaled by 0.2,
+//     and x^0.2 is reused for the derivative 2.2 x^1.2 = 2.2 * x * x^0.2
+//   * constant factors of the image gradient (2/(N*3*H*W), 1/gamma) are applied
+//     once per texel in the epilogue, not per light.
+//
+// The header is plain C++ when compiled without nvcc: tests/hostemu builds it
+// with g++ (float and double) to check the analytic backward against the
+// oracle on the CPU.  That host build is a test harness only; the product has
+// no CPU path.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+
+#if defined(__CUDACC__)
+#define SV_HD __host__ __device__ __forceinline__
+#define SV_D __device__ __forceinline__
+#else
+#define SV_HD inline
+#define SV_D inline
+#endif
+
+namespace svbrdf {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kGamma = 2.2;
+constexpr double kEps = 1e-6;                       // microfacet.py:14
+constexpr double kFresA = -5.55473, kFresB = -6.98316;  // microfacet.py:44
+
+// ---------------------------------------------------------------------------------------------
+// Scalar math: MUFU approximations on the device (1-2 ulp, see DESIGN.md "Numerics"),
+// libm on the host build.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Fm;
+
+template <>
+struct Fm<float> {
+#if defined(__CUDA_ARCH__)
+  static SV_D float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static SV_D float rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static SV_D float sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static SV_D float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static SV_D float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static SV_D float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static SV_D float max(float a, float b) { return fmaxf(a, b); }
+  static SV_D float min(float a, float b) { return fminf(a, b); }
+#else
+  // Host build (tests only).  SV_EMU_MUFU_NOISE perturbs every approximated function by a
+  // pseudo-random relative error of up to +-2^-22 (lg2: absolute), the documented bound of
+  // the MUFU units, so CPU tests can check that the tolerances hold with device-like math.
+#if defined(SV_EMU_MUFU_NOISE)
+  static inline int jitter_mask() {
+    static const int m = [] { const char* e = std::getenv("SV_EMU_NOISE_MASK"); return e ? std::atoi(e) : 31; }();
+    return m;
+  }
+  static inline float jitter(float y, bool absolute = false, int which = 1) {
+    // the device units are exact at their special points: lg2(1) = 0, ex2(0) = 1, rcp(1) = 1, ...
+    if (!std::isfinite(y) || y == 0.0f || y == 1.0f || !(jitter_mask() & which)) return y;
+    static thread_local uint32_t s = 0x9E3779B9u;
+    s = s * 1664525u + 1013904223u;
+    const float u = (float(s >> 8) * (1.0f / 8388608.0f) - 1.0f) * 2.3841858e-7f;   // [-2^-22, 2^-22)
+    return absolute ? y + u * (std::fabs(y) > 1.0f ? std::fabs(y) : 1.0f) : y * (1.0f + u);
+  }
+#else
+  static inline float jitter(float y, bool = false, int = 0) { return y; }
+#endif
+  static SV_HD float rcp(float x) { return jitter(1.0f / x, false, 1); }
+  static SV_HD float rsqrt(float x) { return jitter(1.0f / std::sqrt(x), false, 2); }
+  static SV_HD float sqrt(float x) { return jitter(std::sqrt(x), false, 4); }
+  static SV_HD float lg2(float x) { return jitter(std::log2(x), true, 8); }
+  static SV_HD float ex2(float x) { return jitter(std::exp2(x), false, 16); }
+  static SV_HD float fma(float a, float b, float c) { return std::fma(a, b, c); }
+  static SV_HD float max(float a, float b) { return a > b ? a : b; }
+  static SV_HD float min(float a, float b) { return a < b ? a : b; }
+#endif
+};
+
+template <>
+struct Fm<double> {
+  static SV_HD double rcp(double x) { return 1.0 / x; }
+  static SV_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static SV_HD double sqrt(double x) { return ::sqrt(x); }
+  static SV_HD double lg2(double x) { return ::log2(x); }
+  static SV_HD double ex2(double x) { return ::exp2(x); }
+  static SV_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
+  static SV_HD double max(double a, double b) { return a > b ? a : b; }
+  static SV_HD double min(double a, double b) { return a < b ? a : b; }
+};
+
+// rsqrt with one Newton step: y' = y + (y/2)(1 - x y^2).  MUFU.RSQ is good to ~2 ulp; the cosines
+// n.v, n.h feed 1 - c^2 in the GGX denominator, where for the reference's default (smooth)
+// roughness an error of 2e-7 in c is a 1 % error of the highlight.  The step brings the
+// direction normalisations to <1 ulp, the level of the IEEE sqrt + divide the reference uses.
+#ifndef SV_REFINE_RSQRT
+#define SV_REFINE_RSQRT 1
+#endif
+template <typename T>
+SV_HD T rsqrt_dir(T x) {
+  T y = Fm<T>::rsqrt(x);
+#if SV_REFINE_RSQRT
+  if (sizeof(T) == 4) {
+    const T e = Fm<T>::fma(-x * y, y, T(1));
+    y = Fm<T>::fma(T(0.5) * y, e, y);
+  }
+#endif
+  return y;
+}
+
+// x^2.2 for x in [0,1] as x^2 * x^0.2; also returns r = x^0.2 for the derivative.
+template <typename T>
+SV_HD T pow22(T x, T& r) {
+  r = Fm<T>::ex2(T(0.2) * Fm<T>::lg2(x));
+  return x * x * r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-texel state
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Texel {
+  T px, py;          // texel centre on the sample plane (z = 0), microfacet.py:16-19
+  T n[3];            // unit shading normal, microfacet.py:64-70
+  T kd[3];           // d_c/pi * (1 - s_c), microfacet.py:102-103
+  T s[3];            // specular albedo
+  T a2, k, omk;      // alpha^2, k = alpha/2 + eps, 1 - k  (alpha = rough^2), microfacet.py:30,51,106
+};
+
+template <typename T>
+struct TexelAux {    // needed again only by the epilogue
+  T dpow[7];         // d(x^2.2)/dt = 1.1 * x * x^0.2 for channels 0,1,2,5,6,7,8
+  T d[3];            // diffuse albedo
+  T rough, alpha;
+  T mx, my, mz;      // un-normalised normal (clamped nx, ny, reconstructed nz)
+  T rlen;            // 1/|m|
+  bool in3, in4;     // inner clamp masks on nx, ny (microfacet.py:65-66)
+  bool planar_free;  // nx^2+ny^2 <= 1-eps: the nz path carries gradient (microfacet.py:67)
+};
+
+template <typename T>
+struct Grads {       // accumulated over lights, w.r.t. the Texel fields (unscaled)
+  T kd[3];           // dL/d f1_c   (sum of gf_c)
+  T sF[3];           // dL/d s_c through the Fresnel term
+  T a2, k;
+  T n[3];
+  T pw[3];           // dL/d light_pow_c (only when requested)
+  T loss;            // sum of squared differences (L2 modes)
+};
+
+// Texel centre: ((j + 0.5)/W_full - 0.5) * size in the reference's fp32 op order
+// (microfacet.py:16-19; y is negated, rows index y).
+template <typename T>
+SV_HD void texel_position(int row, int col, int res, float size, T& px, T& py) {
+  const float fx = ((float(col) + 0.5f) / float(res) - 0.5f) * size;
+  const float fy = ((float(row) + 0.5f) / float(res) - 0.5f) * size;
+  px = T(fx);
+  py = T(-fy);
+}
+
+// Prologue: 9 channels -> material parameters.  `t` must already be clamped to [-1,1]
+// by the caller when the outer clamp of svbrdf.py:60 applies.
+template <typename T>
+SV_HD void texel_prologue(const T t[9], Texel<T>& tx, TexelAux<T>& ax) {
+  const T inv_pi = T(1.0 / kPi);
+  T r;
+  T x;
+  for (int c = 0; c < 3; ++c) {
+    x = (t[c] + T(1)) * T(0.5);
+    ax.d[c] = pow22(x, r);
+    ax.dpow[c] = T(0.5 * kGamma) * x * r;
+    x = (t[6 + c] + T(1)) * T(0.5);
+    tx.s[c] = pow22(x, r);
+    ax.dpow[4 + c] = T(0.5 * kGamma) * x * r;
+    tx.kd[c] = ax.d[c] * inv_pi * (T(1) - tx.s[c]);
+  }
+  x = (t[5] + T(1)) * T(0.5);
+  ax.rough = pow22(x, r);
+  ax.dpow[3] = T(0.5 * kGamma) * x * r;
+  ax.alpha = ax.rough * ax.rough;
+  tx.a2 = ax.alpha * ax.alpha;
+  tx.k = ax.alpha * T(0.5) + T(kEps);
+  tx.omk = T(1) - tx.k;
+
+  ax.in3 = (t[3] >= T(-1)) && (t[3] <= T(1));
+  ax.in4 = (t[4] >= T(-1)) && (t[4] <= T(1));
+  ax.mx = Fm<T>::min(Fm<T>::max(t[3], T(-1)), T(1));
+  ax.my = Fm<T>::min(Fm<T>::max(t[4], T(-1)), T(1));
+  const T planar = ax.mx * ax.mx + ax.my * ax.my;
+  const T cap = T(1) - T(kEps);
+  ax.planar_free = planar <= cap;
+  const T pc = Fm<T>::min(planar, cap);
+  ax.mz = Fm<T>::sqrt(T(1) - pc);
+  ax.rlen = rsqrt_dir(ax.mx * ax.mx + ax.my * ax.my + ax.mz * ax.mz);
+  tx.n[0] = ax.mx * ax.rlen;
+  tx.n[1] = ax.my * ax.rlen;
+  tx.n[2] = ax.mz * ax.rlen;
+}
+
+template <typename T>
+SV_HD void grads_zero(Grads<T>& g) {
+  for (int c = 0; c < 3; ++c) g.kd[c] = g.sF[c] = g.n[c] = g.pw[c] = T(0);
+  g.a2 = g.k = g.loss = T(0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One light.  Modes:
+//   kRender  : forward only, returns the 3 gamma-encoded channels in `out`
+//   kVjp     : `io` holds the upstream dL/d out_c (mode B backward)
+//   kL2      : `io` holds the target image; accumulates (out - target)^2 and its gradient
+// Gradients are accumulated WITHOUT the constant image-gradient factor (see epilogue).
+// ---------------------------------------------------------------------------------------------
+enum LightMode { kRender = 0, kVjp = 1, kL2 = 2 };
+
+template <typename T>
+struct LightGeom {   // per light, texture independent
+  T cx, cy, cz, cz2; // camera position, cz^2
+  T lx, ly, lz, lz2; // light position, lz^2 (unused when co-located)
+};
+
+template <typename T, int MODE, bool COLOC, bool WANT_POW>
+SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T pw[3], const T io[3], T out[3], Grads<T>& g) {
+  typedef Fm<T> F;
+  // --- geometry (microfacet.py:91-99) ---
+  const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
+  const T vv = F::fma(Vx, Vx, F::fma(Vy, Vy, lg.cz2));
+  const T rv = rsqrt_dir(vv);
+  const T nV = F::fma(tx.n[0], Vx, F::fma(tx.n[1], Vy, tx.n[2] * Vz));
+  const T ndv_raw = nV * rv;
+  T Lx, Ly, Lz, rl, ndl_raw, ndh_raw, vdh, rh, inv_d2;
+  if (COLOC) {
+    // light == camera: l = v = h, v.h = 1
+    Lx = Vx; Ly = Vy; Lz = Vz;
+    rl = rv;
+    ndl_raw = ndv_raw;
+    ndh_raw = ndv_raw;
+    vdh = T(1);
+    rh = T(0.5);
+    inv_d2 = rv * rv;
+  } else {
+    Lx = lg.lx - tx.px; Ly = lg.ly - tx.py; Lz = lg.lz;
+    const T d2 = F::fma(Lx, Lx, F::fma(Ly, Ly, lg.lz2));
+    rl = rsqrt_dir(d2);
+    inv_d2 = rl * rl;
+    const T nL = F::fma(tx.n[0], Lx, F::fma(tx.n[1], Ly, tx.n[2] * Lz));
+    ndl_raw = nL * rl;
+    const T lv = F::fma(Lx, Vx, F::fma(Ly, Vy, Lz * Vz)) * (rl * rv);
+    const T opl = T(1) + lv;               // |l+v|^2 / 2
+    rh = rsqrt_dir(opl + opl);
+    ndh_raw = (ndl_raw + ndv_raw) * rh;
+    vdh = F::max(opl * rh, T(0));
+  }
+  const T ndv = F::max(ndv_raw, T(0));
+  const T ndl = F::max(ndl_raw, T(0));
+  const T ndh = F::max(ndh_raw, T(0));
+
+  // --- GGX (microfacet.py:28-32) ---
+  const T c2 = ndh * ndh;
+  const T den = F::fma(c2, tx.a2, T(1) - c2);
+  const T Dd = F::fma(T(kPi) * den, den, T(kEps));
+  const T rDd = F::rcp(Dd);
+  const T D = tx.a2 * rDd;
+  // --- Fresnel (microfacet.py:43-45) ---
+  T sphg;
+  if (COLOC) {
+    sphg = T(1.6815857857725708e-4);       // 2^(-5.55473 - 6.98316)
+  } else {
+    sphg = F::ex2(F::fma(T(kFresA), vdh, T(kFresB)) * vdh);
+  }
+  // --- Smith (microfacet.py:47-52) ---
+  const T gv = F::fma(ndv, tx.omk, tx.k);
+  const T gl = COLOC ? gv : F::fma(ndl, tx.omk, tx.k);
+  const T rgv = F::rcp(gv);
+  const T rgl = COLOC ? rgv : F::rcp(gl);
+  const T A = ndv * rgv;
+  const T B = ndl * rgl;
+  const T G = A * B;
+  // --- specular lobe (microfacet.py:109) ---
+  const T q = F::fma(T(4) * ndv, ndl, T(kEps));
+  const T rq = F::rcp(q);
+  const T DGq = D * rq;                    // D/q
+  const T Q = DGq * G;
+  // --- radiance, clamp, gamma (microfacet.py:112-120) ---
+  const T w = ndl * inv_d2;
+  T f[3], I[3], Icl[3], lgI[3];
+  for (int c = 0; c < 3; ++c) {
+    const T Fc = F::fma(T(1) - tx.s[c], sphg, tx.s[c]);
+    f[c] = F::fma(Q, Fc, tx.kd[c]);
+    I[c] = pw[c] * f[c] * w;
+    Icl[c] = F::min(F::max(I[c], T(kEps)), T(1));
+    lgI[c] = F::lg2(Icl[c]);
+  }
+  if (MODE == kRender) {
+    for (int c = 0; c < 3; ++c) out[c] = F::ex2(lgI[c] * T(1.0 / kGamma));
+    return;
+  }
+
+  // --- image gradient without its constant factor ---
+  T gI[3];
+  for (int c = 0; c < 3; ++c) {
+    T up;
+    if (MODE == kL2) {
+      const T o = F::ex2(lgI[c] * T(1.0 / kGamma));
+      const T diff = o - io[c];
+      g.loss = F::fma(diff, diff, g.loss);
+      up = diff;
+    } else {
+      up = io[c];
+    }
+    // d out / d I = (1/gamma) * Icl^(1/gamma - 1), zero outside the clamp (inclusive edges)
+    const T slope = F::ex2(lgI[c] * T(1.0 / kGamma - 1.0));
+    gI[c] = (I[c] == Icl[c]) ? up * slope : T(0);
+  }
+
+  // --- back through the radiance ---
+  T gw = T(0), gQ = T(0);
+  const T oms_sphg = T(1) - sphg;
+  for (int c = 0; c < 3; ++c) {
+    const T tc = gI[c] * f[c];
+    gw = F::fma(tc, pw[c], gw);
+    if (WANT_POW) g.pw[c] = F::fma(tc, w, g.pw[c]);
+    const T gf = gI[c] * pw[c] * w;
+    g.kd[c] += gf;
+    const T Fc = F::fma(T(1) - tx.s[c], sphg, tx.s[c]);
+    gQ = F::fma(gf, Fc, gQ);
+    g.sF[c] = F::fma(gf * Q, oms_sphg, g.sF[c]);
+  }
+  // Q = D*G/q
+  const T gD = gQ * G * rq;
+  const T gG = gQ * DGq;
+  const T gq = -gQ * Q * rq;
+  // D = a2/Dd, Dd = pi*den^2 + eps, den = c2*a2 + 1 - c2
+  const T gden = -gD * D * rDd * T(2.0 * kPi) * den;
+  g.a2 += F::fma(gden, c2, gD * rDd);
+  const T gndh = gden * (tx.a2 - T(1)) * (ndh + ndh);
+  // G = A*B, A = ndv/gv, B = ndl/gl
+  const T rgv2 = rgv * rgv, rgl2 = rgl * rgl;
+  const T gA = gG * B, gB = gG * A;
+  const T gndv = F::fma(gA * tx.k, rgv2, gq * T(4) * ndl);
+  const T gndl = F::fma(gB * tx.k, rgl2, F::fma(gq * T(4), ndv, gw * inv_d2));
+  g.k -= F::fma(gA * ndv * (T(1) - ndv), rgv2, gB * ndl * (T(1) - ndl) * rgl2);
+  // clamp(min=0) masks are inclusive; n.h = (n.l + n.v) * rh
+  const T mv = (ndv_raw >= T(0)) ? gndv : T(0);
+  const T ml = (ndl_raw >= T(0)) ? gndl : T(0);
+  const T mh = (ndh_raw >= T(0)) ? gndh * rh : T(0);
+  if (COLOC) {
+    const T cV = (mv + ml + mh + mh) * rv;
+    g.n[0] = F::fma(cV, Vx, g.n[0]);
+    g.n[1] = F::fma(cV, Vy, g.n[1]);
+    g.n[2] = F::fma(cV, Vz, g.n[2]);
+  } else {
+    const T cV = (mv + mh) * rv;
+    const T cL = (ml + mh) * rl;
+    g.n[0] = F::fma(cV, Vx, F::fma(cL, Lx, g.n[0]));
+    g.n[1] = F::fma(cV, Vy, F::fma(cL, Ly, g.n[1]));
+    g.n[2] = F::fma(cV, Vz, F::fma(cL, Lz, g.n[2]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue: gradients w.r.t. material parameters -> gradients w.r.t. the 9 channels.
+// `scale` is the constant image-gradient factor (2/(N*3*H*W*gamma) for L2, 1/gamma for VJP).
+// `outer` = mask of the caller's clamp(-1,1) on the raw parameter (svbrdf.py:60); pass all-true
+// when the clamp belongs to the caller's graph (mode B).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const Grads<T>& g, T scale, const bool outer[9], T gt[9]) {
+  typedef Fm<T> F;
+  const T inv_pi = T(1.0 / kPi);
+  for (int c = 0; c < 3; ++c) {
+    const T gd = g.kd[c] * (T(1) - tx.s[c]) * inv_pi;
+    const T gs = F::fma(-g.kd[c], ax.d[c] * inv_pi, g.sF[c]);
+    gt[c] = gd * ax.dpow[c];
+    gt[6 + c] = gs * ax.dpow[4 + c];
+  }
+  // a2 = alpha^2, k = alpha/2 + eps, alpha = rough^2
+  const T galpha = F::fma(g.a2, ax.alpha + ax.alpha, g.k * T(0.5));
+  gt[5] = galpha * (ax.rough + ax.rough) * ax.dpow[3];
+  // n = m/|m|
+  const T ndg = F::fma(tx.n[0], g.n[0], F::fma(tx.n[1], g.n[1], tx.n[2] * g.n[2]));
+  const T gmx = (g.n[0] - tx.n[0] * ndg) * ax.rlen;
+  const T gmy = (g.n[1] - tx.n[1] * ndg) * ax.rlen;
+  const T gmz = (g.n[2] - tx.n[2] * ndg) * ax.rlen;
+  // mz = sqrt(1 - clamp(mx^2+my^2, 0, 1-eps))
+  const T gplanar = ax.planar_free ? -gmz * T(0.5) * F::rcp(ax.mz) : T(0);
+  gt[3] = ax.in3 ? F::fma(gplanar, ax.mx + ax.mx, gmx) : T(0);
+  gt[4] = ax.in4 ? F::fma(gplanar, ax.my + ax.my, gmy) : T(0);
+  for (int kk = 0; kk < 9; ++kk) gt[kk] = outer[kk] ? gt[kk] * scale : T(0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch/optim/adam.py:531-547, single-tensor path, amsgrad off, weight decay 0).
+//   m <- m + (g - m)(1 - b1);  v <- v*b2 + (1 - b2) g^2;
+//   p <- p - step_size * m / (sqrt(v)/sqrt(bc2) + eps),  step_size = lr/bc1
+// The host passes step_size and 1/sqrt(bc2) computed in double like torch does.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct AdamStep {
+  T one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps;
+};
+
+template <typename T>
+SV_HD void adam_update(T& p, T& m, T& v, T g, const AdamStep<T>& a) {
+  typedef Fm<T> F;
+  m = F::fma(g - m, a.one_minus_b1, m);
+  v = F::fma(a.one_minus_b2 * g, g, v * a.b2);
+  const T denom = F::fma(F::sqrt(v), a.inv_sqrt_bc2, a.eps);
+  p = F::fma(-a.step_size * m, F::rcp(denom), p);
+}
+
+}  // namespace svbrdf

@@ -1,0 +1,61 @@
+"""Drop-in for the two workflows of the reference's ``src/scripts.py`` that sit on the hot path:
+``optim_perpixel`` (scripts.py:67-97) and the forward-only ``render`` (scripts.py:31-41).
+
+Same signatures and files written; the device is ``cuda:0`` — unlike the reference
+(scripts.py:68) there is no CPU branch: without a GPU the call raises.
+"""
+
+from __future__ import annotations
+
+import torch as th
+
+from .microfacet import Microfacet
+from .svbrdf import SvbrdfIO, SvbrdfOptim
+
+
+def _device():
+    if not th.cuda.is_available():
+        raise RuntimeError("svbrdf_diff_renderer_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return th.device("cuda:0")
+
+
+def render(json_dir, res):
+    device = _device()
+    svbrdf_obj = SvbrdfIO(json_dir, device)
+    textures = svbrdf_obj.load_textures_th(svbrdf_obj.reference_dir, res)
+    render_obj = Microfacet(res, svbrdf_obj.n_of_imgs, svbrdf_obj.im_size, svbrdf_obj.cl, device)
+    with th.no_grad():
+        rendereds = render_obj.eval(textures)
+    svbrdf_obj.save_images_th(rendereds, svbrdf_obj.target_dir)
+
+
+def optim_perpixel(json_dir, res, lr, epochs, tex_init, optim_light=False, uint8_targets=False):
+    device = _device()
+
+    svbrdf_obj = SvbrdfIO(json_dir, device)
+    targets = svbrdf_obj.load_images_th(svbrdf_obj.target_dir, res, as_uint8=uint8_targets)
+
+    renderer_obj = Microfacet(res, svbrdf_obj.n_of_imgs, svbrdf_obj.im_size, svbrdf_obj.cl, device)
+
+    optim_obj = SvbrdfOptim(device, renderer_obj)
+    optim_obj.load_targets(targets)
+
+    if tex_init == "random":
+        optim_obj.init_from_randn()
+    elif tex_init == "const":
+        optim_obj.init_from_const()
+    elif tex_init == "textures":
+        optim_obj.init_from_tex(svbrdf_obj.load_textures_th(svbrdf_obj.reference_dir, res))
+    else:
+        raise ValueError(f"tex_init must be 'random', 'const' or 'textures', got {tex_init!r}")
+
+    optim_obj.optim(epochs, lr, svbrdf_obj, optim_light)
+
+    with th.no_grad():
+        maps = optim_obj.textures.detach().clamp(-1, 1)
+        svbrdf_obj.save_textures_th(maps, svbrdf_obj.optimize_dir)
+        if optim_light:
+            print("Optimized light: ", svbrdf_obj.cl[2])
+            renderer_obj.update_light(svbrdf_obj.cl[2])
+        svbrdf_obj.save_images_th(renderer_obj.eval(maps), svbrdf_obj.rerender_dir)
+    return optim_obj

@@ -1,0 +1,113 @@
+// TEST HARNESS ONLY — host build of csrc/svbrdf_core.cuh (the per-texel math the CUDA
+// kernels instantiate), in float (libm in place of MUFU) and in double.
+//
+// Purpose: check the analytic backward / Adam restatement against the oracle on a
+// machine without a GPU (`pytest -m "not gpu"`).  Nothing in the product imports,
+// links or loads this file; the product has no CPU path.
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "../../svbrdf_diff_renderer_b200/csrc/svbrdf_core.cuh"
+
+using namespace svbrdf;
+
+namespace {
+
+template <typename T>
+LightGeom<T> geom(const T* cam, const T* light, int i) {
+  LightGeom<T> g;
+  g.cx = cam[3 * i]; g.cy = cam[3 * i + 1]; g.cz = cam[3 * i + 2]; g.cz2 = g.cz * g.cz;
+  g.lx = light[3 * i]; g.ly = light[3 * i + 1]; g.lz = light[3 * i + 2]; g.lz2 = g.lz * g.lz;
+  return g;
+}
+
+// mode: 0 render, 1 vjp, 2 l2 grad, 3 l2 + adam
+template <typename T, bool COLOC>
+void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size, int res, int row0, int rows, int W,
+         int N, int n_total, const T* io, T* out, T* grad_tex, T* grad_pow, double* loss, int outer_clamp, T* m, T* v,
+         const double* adam) {
+  const size_t plane = size_t(rows) * W;
+  double loss_acc = 0.0, gp_acc[3] = {0, 0, 0};
+  T scale;
+  if (mode == 1) scale = T(1.0 / kGamma);
+  else scale = T(2.0 / (double(n_total) * 3.0 * double(res) * double(res) * kGamma));
+  for (int r = 0; r < rows; ++r) {
+    for (int c = 0; c < W; ++c) {
+      const size_t p = size_t(r) * W + c;
+      T t[9];
+      bool outer[9];
+      for (int k = 0; k < 9; ++k) {
+        const T raw = tex[k * plane + p];
+        if (outer_clamp) {
+          outer[k] = raw >= T(-1) && raw <= T(1);
+          t[k] = Fm<T>::min(Fm<T>::max(raw, T(-1)), T(1));
+        } else {
+          outer[k] = true;
+          t[k] = raw;
+        }
+      }
+      Texel<T> tx;
+      TexelAux<T> ax;
+      texel_position(row0 + r, c, res, size, tx.px, tx.py);
+      texel_prologue(t, tx, ax);
+      Grads<T> g;
+      grads_zero(g);
+      for (int i = 0; i < N; ++i) {
+        const LightGeom<T> lg = geom(cam, light, i);
+        T in3[3] = {0, 0, 0}, o3[3];
+        if (mode >= 1)
+          for (int ch = 0; ch < 3; ++ch) in3[ch] = io[(size_t(i) * 3 + ch) * plane + p];
+        if (mode == 0) {
+          shade_light<T, kRender, COLOC, false>(tx, lg, pw, in3, o3, g);
+          for (int ch = 0; ch < 3; ++ch) out[(size_t(i) * 3 + ch) * plane + p] = o3[ch];
+        } else if (mode == 1) {
+          shade_light<T, kVjp, COLOC, true>(tx, lg, pw, in3, o3, g);
+        } else {
+          shade_light<T, kL2, COLOC, true>(tx, lg, pw, in3, o3, g);
+        }
+      }
+      if (mode == 0) continue;
+      T gt[9];
+      texel_epilogue(tx, ax, g, scale, outer, gt);
+      loss_acc += double(g.loss);
+      for (int ch = 0; ch < 3; ++ch) gp_acc[ch] += double(g.pw[ch]) * double(scale);
+      if (mode == 3) {
+        AdamStep<T> a;
+        a.one_minus_b1 = T(adam[0]); a.b2 = T(adam[1]); a.one_minus_b2 = T(adam[2]);
+        a.step_size = T(adam[3]); a.inv_sqrt_bc2 = T(adam[4]); a.eps = T(adam[5]);
+        for (int k = 0; k < 9; ++k) adam_update(tex[k * plane + p], m[k * plane + p], v[k * plane + p], gt[k], a);
+      } else {
+        for (int k = 0; k < 9; ++k) grad_tex[k * plane + p] = gt[k];
+      }
+    }
+  }
+  if (loss) *loss = loss_acc / (double(n_total) * 3.0 * double(res) * double(res));
+  if (grad_pow) for (int ch = 0; ch < 3; ++ch) grad_pow[ch] = T(gp_acc[ch]);
+}
+
+template <typename T>
+void dispatch(int coloc, int mode, T* tex, const T* cam, const T* light, const T* pw, float size, int res, int row0,
+              int rows, int W, int N, int n_total, const T* io, T* out, T* grad_tex, T* grad_pow, double* loss,
+              int outer_clamp, T* m, T* v, const double* adam) {
+  if (coloc) run<T, true>(mode, tex, cam, light, pw, size, res, row0, rows, W, N, n_total, io, out, grad_tex, grad_pow, loss, outer_clamp, m, v, adam);
+  else run<T, false>(mode, tex, cam, light, pw, size, res, row0, rows, W, N, n_total, io, out, grad_tex, grad_pow, loss, outer_clamp, m, v, adam);
+}
+
+}  // namespace
+
+extern "C" {
+
+void emu_run_f32(int coloc, int mode, float* tex, const float* cam, const float* light, const float* pw, float size,
+                 int res, int row0, int rows, int W, int N, int n_total, const float* io, float* out, float* grad_tex,
+                 float* grad_pow, double* loss, int outer_clamp, float* m, float* v, const double* adam) {
+  dispatch<float>(coloc, mode, tex, cam, light, pw, size, res, row0, rows, W, N, n_total, io, out, grad_tex, grad_pow, loss, outer_clamp, m, v, adam);
+}
+
+void emu_run_f64(int coloc, int mode, double* tex, const double* cam, const double* light, const double* pw, float size,
+                 int res, int row0, int rows, int W, int N, int n_total, const double* io, double* out, double* grad_tex,
+                 double* grad_pow, double* loss, int outer_clamp, double* m, double* v, const double* adam) {
+  dispatch<double>(coloc, mode, tex, cam, light, pw, size, res, row0, rows, W, N, n_total, io, out, grad_tex, grad_pow, loss, outer_clamp, m, v, adam);
+}
+
+}  // extern "C"

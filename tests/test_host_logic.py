@@ -1,0 +1,105 @@
+"""CPU: host-side logic of the drop-in package — no kernels are launched."""
+import json
+
+import numpy as np
+import pytest
+import torch as th
+
+import svbrdf_diff_renderer_b200 as pkg
+from svbrdf_diff_renderer_b200 import synth
+from svbrdf_diff_renderer_b200.imageio import imread, imwrite
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.Microfacet(16, 9, synth.IM_SIZE_CM, synth.calibration(9), th.device("cpu"))
+    if not th.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pkg.optim_perpixel(None, 16, 0.01, 1, "random")
+
+
+def test_cpu_tensors_are_rejected_by_the_native_binding():
+    from svbrdf_diff_renderer_b200 import _native as nv
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        nv.dev_f32(th.zeros(4), "x")
+    with pytest.raises(RuntimeError, match="unsupported dtype"):
+        nv.target_dtype_code(th.zeros(2, dtype=th.float64))
+    assert nv.target_dtype_code(th.zeros(2, dtype=th.uint8)) == nv.TARGET_U8
+
+
+def test_synthetic_inputs_are_reproducible_and_in_range():
+    a, b = synth.random_textures(32, 4), synth.random_textures(32, 4)
+    assert th.equal(a, b) and a.shape == (1, 9, 32, 32) and a.dtype == th.float32
+    assert float(a.min()) >= -1 and float(a.max()) <= 1
+    assert not th.equal(a, synth.random_textures(32, 5))
+    for n in (9, 64, 256):
+        cl = synth.calibration(n)
+        assert cl[0].shape == (n, 3) and th.equal(cl[0], cl[1]) and cl[2].tolist() == [1500.0] * 3
+    off = synth.calibration(9, colocated=False)
+    assert not th.equal(off[0], off[1]) and float(off[1][:, 2].min()) >= 4.0
+    with pytest.raises(ValueError):
+        synth.grid_lights(10)
+
+
+def _write_config(tmp_path, n=9):
+    cl = synth.calibration(n)
+    cfg = {"reference_dir": "target/maps", "target_dir": "target", "optimize_dir": "optim", "rerender_dir": "optim/rerender",
+           "im_size": synth.IM_SIZE_CM, "idx": list(range(n)), "camera_pos": cl[0].tolist(), "light_pos": cl[1].tolist(),
+           "light_pow": list(synth.LIGHT_POW)}
+    p = tmp_path / "cfg.json"
+    p.write_text(json.dumps(cfg))
+    return p
+
+
+def test_svbrdfio_config_and_png_round_trip(tmp_path):
+    io = pkg.SvbrdfIO(_write_config(tmp_path), th.device("cpu"))
+    assert io.n_of_imgs == 9 and io.im_size == synth.IM_SIZE_CM
+    assert th.equal(io.cl[0], synth.calibration(9)[0]) and io.cl[2].tolist() == [1500.0] * 3
+
+    # images: float32 and uint8 ingest agree exactly (x/255)
+    imgs = th.rand(9, 3, 16, 16)
+    io.save_images_th(imgs, io.target_dir)
+    assert (io.target_dir / "all.png").exists()
+    f32 = io.load_images_th(io.target_dir, 16)
+    u8 = io.load_images_th(io.target_dir, 16, as_uint8=True)
+    assert f32.dtype == th.float32 and u8.dtype == th.uint8 and f32.shape == (9, 3, 16, 16)
+    assert th.equal(u8.float() / 255, f32)
+    assert float((f32 - imgs).abs().max()) <= 1 / 255 + 1e-6       # 8-bit quantisation (truncating, imageio.py:71)
+
+    # textures: save -> load returns the quantised maps in the [1,9,R,R] channel order
+    tex = synth.random_textures(16, 3)
+    io.save_textures_th(tex, io.reference_dir)
+    for name in ("nom.png", "dif.png", "spe.png", "rgh.png", "tex.png"):
+        assert (io.reference_dir / name).exists()
+    back = io.load_textures_th(io.reference_dir, 16)
+    assert back.shape == (1, 9, 16, 16)
+    assert float((back[:, [0, 1, 2, 5, 6, 7, 8]] - tex[:, [0, 1, 2, 5, 6, 7, 8]]).abs().max()) <= 2 / 255 + 1e-6
+    assert float((back[:, 3:5] - tex[:, 3:5]).abs().max()) <= 0.02
+
+    with pytest.raises(FileNotFoundError):
+        pkg.SvbrdfIO(tmp_path / "missing.json", th.device("cpu"))
+
+
+def test_imageio_flags(tmp_path):
+    im = np.random.default_rng(0).random((8, 8, 3)).astype("float32")
+    imwrite(im, tmp_path / "a.png", "srgb")
+    back = imread(tmp_path / "a.png", "srgb")
+    assert back.shape == (8, 8, 3) and np.abs(back - im).max() <= 1 / 255 + 1e-6
+    rough = imread(tmp_path / "a.png", "rough")
+    assert rough.shape == (8, 8)
+    nrm = imread(tmp_path / "a.png", "normal")
+    assert np.allclose(np.linalg.norm(nrm, axis=2), 1, atol=1e-5)
+    up = imread(tmp_path / "a.png", "srgb", (16, 16))
+    assert up.shape == (16, 16, 3)
+
+
+def test_optim_base_class_api():
+    base = pkg.Optim(th.device("cpu"), None)
+    leaf = base.gradient(th.zeros(3))
+    assert leaf.requires_grad and leaf.is_leaf
+    lst = base.gradient([th.zeros(2), th.ones(2)])
+    assert all(t.requires_grad for t in lst)
+    with pytest.raises(NotImplementedError):
+        base.load_targets(None)
+    with pytest.raises(NotImplementedError):
+        base.optim(1, 0.1, None, False)

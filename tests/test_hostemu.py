@@ -1,0 +1,94 @@
+"""CPU: the per-texel math the CUDA kernels instantiate (csrc/svbrdf_core.cuh), built for the
+host in double and float, against the reference-generated golden vectors.
+
+double: proves the analytic backward, the half-vector-free geometry, the co-located fast path
+and the fused Adam are exact restatements (agreement ~1e-12 with the reference's fp64 autograd).
+float : same code path the GPU runs (libm instead of MUFU) held to the tolerance the GPU tests use.
+"""
+import numpy as np
+import pytest
+
+from tests import hostemu as E
+from tests import parity
+
+
+def _args(g, power_key="power_render"):
+    return g["cam"], g["light"], g[power_key], float(g["size"]), int(g["res"])
+
+
+@pytest.mark.parametrize("name", parity.CASES)
+def test_double_is_exact(name):
+    g = parity.golden(name)
+    out = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g), dtype=np.float64)["out"]
+    np.testing.assert_allclose(out, g["render_gt_f64"], rtol=2e-11, atol=1e-13)
+
+    v = E.run(E.MODE_VJP, np.clip(g["tex0"][0], -1, 1), *_args(g), io=g["grad_img"], dtype=np.float64)
+    assert parity.max_err(v["grad_tex"], g["vjp_tex_f64"][0]) < 1e-11
+    assert parity.max_err(v["grad_pow"], g["vjp_pow_f64"]) < 1e-11
+
+    l2 = E.run(E.MODE_L2, g["tex0"][0], *_args(g, "power"), io=g["target"], dtype=np.float64, outer_clamp=True)
+    assert parity.max_err(l2["grad_tex"], g["grad0_f64"][0]) < 1e-11
+    assert l2["loss"] == pytest.approx(float(g["loss_f64"][0]), rel=1e-12)
+    if g["gpow0_f64"].size:
+        assert parity.max_err(l2["grad_pow"], g["gpow0_f64"]) < 1e-11
+
+
+@pytest.mark.parametrize("noise", [False, True], ids=["libm", "mufu-noise"])
+@pytest.mark.parametrize("name", parity.CASES)
+def test_float_within_reference_noise(name, noise):
+    g = parity.golden(name)
+    strict = name.startswith("wellcond")
+    out = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g), noise=noise)["out"]
+    parity.check_against_arbiter(out, g["target"], g["render_gt_f64"], parity.RTOL_RENDER, f"{name} render", strict=strict, pure_relative=True)
+    l2 = E.run(E.MODE_L2, g["tex0"][0], *_args(g, "power"), io=g["target"], outer_clamp=True, noise=noise)
+    parity.check_against_arbiter(l2["grad_tex"], g["grad0_f32"][0], g["grad0_f64"][0], parity.RTOL_GRAD, f"{name} grad", strict=strict)
+    assert l2["loss"] == pytest.approx(float(g["loss_f64"][0]), rel=1e-5)
+    v = E.run(E.MODE_VJP, np.clip(g["tex0"][0], -1, 1), *_args(g), io=g["grad_img"], noise=noise)
+    parity.check_against_arbiter(v["grad_tex"], g["vjp_tex_f32"][0], g["vjp_tex_f64"][0], parity.RTOL_GRAD, f"{name} vjp", strict=strict)
+
+
+def _adam_run(g, dtype, epochs, noise=False):
+    tex = np.ascontiguousarray(g["tex0"][0], dtype=dtype)
+    m, v = np.zeros_like(tex), np.zeros_like(tex)
+    losses = []
+    for step in range(1, epochs + 1):
+        r = E.run(E.MODE_ADAM, tex, *_args(g, "power"), io=g["target"], dtype=dtype, outer_clamp=True, m=m, v=v,
+                  adam=E.adam_scalars(step, float(g["lr"])), noise=noise)
+        losses.append(r["loss"])
+    return tex, np.array(losses)
+
+
+@pytest.mark.parametrize("name", ["coloc_32x9", "offaxis_32x9", "edges_32x9"])
+def test_fused_adam_double_tracks_reference(name):
+    g = parity.golden(name)
+    maps, losses = _adam_run(g, np.float64, int(g["epochs"]))
+    np.testing.assert_allclose(losses, g["loss_f64"], rtol=1e-10)
+    # Adam's +-lr first steps amplify 1e-16 gradient noise where g ~ 0: allow 1e-7 absolute
+    assert np.abs(maps - g["maps_f64"][0]).max() < 1e-7
+
+
+@pytest.mark.parametrize("noise", [False, True], ids=["libm", "mufu-noise"])
+@pytest.mark.parametrize("name", ["coloc_32x9", "offaxis_32x9", "wellcond_32x9"])
+def test_fused_adam_float_within_tolerance(name, noise):
+    g = parity.golden(name)
+    maps, losses = _adam_run(g, np.float32, int(g["epochs"]), noise)
+    np.testing.assert_allclose(losses, g["loss_f64"], rtol=2e-5)
+    e_x, e_ref, frac = parity.check_against_arbiter(maps, g["maps_f32"][0], g["maps_f64"][0], parity.RTOL_GRAD, f"{name} maps",
+                                                    floor=2e-4, min_fraction=0.998)
+
+
+def test_row_band_equals_full():
+    g = parity.golden("coloc_32x9")
+    full = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g))["out"]
+    band = E.run(E.MODE_RENDER, np.ascontiguousarray(g["tex_gt"][0][:, 8:20, :]), *_args(g), row0=8)["out"]
+    assert np.array_equal(band, full[:, :, 8:20, :])
+
+
+def test_u8_division_is_correctly_rounded():
+    """The in-kernel u8 decode (q = b*r; q += fma(-q,255,b)*r) must equal float32(b)/255 bit for bit."""
+    b = np.arange(256, dtype=np.float32)
+    r = np.float32(1.0) / np.float32(255.0)
+    q = b * r
+    resid = (b.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)      # fma(-q,255,b): exact in fp64
+    fixed = (q.astype(np.float64) + resid.astype(np.float64) * np.float64(r)).astype(np.float32)
+    assert np.array_equal(fixed, b / np.float32(255.0))
