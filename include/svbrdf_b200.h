@@ -68,7 +68,9 @@ typedef struct svbrdf_adam_t {
 int svbrdf_abi_version(void);
 const char* svbrdf_error_string(int code);
 
-/* Bytes of scratch (per concurrent call) the entry points below need for block partials. */
+/* Bytes of scratch (per concurrent call) the entry points below need: block partials plus a finish
+ * counter.  The caller zero-fills it ONCE after allocation (cudaMemset); every call leaves the counter
+ * at zero again, so the same workspace can be reused by consecutive calls on one stream. */
 size_t svbrdf_workspace_bytes(int32_t res, int32_t rows);
 
 /* Microfacet.eval forward (microfacet.py:84-120):  tex [9,rows,res] -> out [N,3,rows,res]. */

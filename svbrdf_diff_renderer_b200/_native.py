@@ -143,7 +143,8 @@ def ptr(t) -> ctypes.c_void_p:
 
 def workspace(res: int, rows: int, device) -> th.Tensor:
     nbytes = lib().svbrdf_workspace_bytes(res, rows)
-    return th.empty(max(nbytes // 4, 4), dtype=th.float32, device=device)
+    # zero-initialised once: the trailing finish counter must be 0 before the first launch (kernels leave it 0)
+    return th.zeros(max(nbytes // 4, 4), dtype=th.float32, device=device)
 
 
 def target_dtype_code(t: th.Tensor) -> int:

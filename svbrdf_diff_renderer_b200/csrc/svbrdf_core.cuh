@@ -131,12 +131,18 @@ SV_HD T pow22(T x, T& r) {
 // ---------------------------------------------------------------------------------------------
 // Per-texel state
 // ---------------------------------------------------------------------------------------------
+// 2^(-5.55473 - 6.98316): the Fresnel term of a co-located light/camera pair (v.h = 1).
+constexpr double kSphgColoc = 1.6815857857725708e-4;
+
 template <typename T>
 struct Texel {
   T px, py;          // texel centre on the sample plane (z = 0), microfacet.py:16-19
   T n[3];            // unit shading normal, microfacet.py:64-70
-  T kd[3];           // d_c/pi * (1 - s_c), microfacet.py:102-103
-  T s[3];            // specular albedo
+  // the light power pw_c (microfacet.py:117) is folded into the per-texel albedo terms:
+  T kdp[3];          // pw_c * d_c/pi * (1 - s_c)            (lambert, microfacet.py:102-103)
+  T sp[3];           // pw_c * s_c
+  T omsp[3];         // pw_c * (1 - s_c)                     (Fresnel: F_c*pw_c = sp + omsp*sphg)
+  T Fp[3];           // pw_c * F_c for a co-located pair (constant per texel)
   T a2, k, omk;      // alpha^2, k = alpha/2 + eps, 1 - k  (alpha = rough^2), microfacet.py:30,51,106
 };
 
@@ -144,6 +150,7 @@ template <typename T>
 struct TexelAux {    // needed again only by the epilogue
   T dpow[7];         // d(x^2.2)/dt = 1.1 * x * x^0.2 for channels 0,1,2,5,6,7,8
   T d[3];            // diffuse albedo
+  T oms[3];          // 1 - s_c
   T rough, alpha;
   T mx, my, mz;      // un-normalised normal (clamped nx, ny, reconstructed nz)
   T rlen;            // 1/|m|
@@ -152,16 +159,16 @@ struct TexelAux {    // needed again only by the epilogue
 };
 
 template <typename T>
-struct Grads {       // accumulated over lights, w.r.t. the Texel fields (unscaled)
-  T kd[3];           // dL/d f1_c   (sum of gf_c)
-  T sF[3];           // dL/d s_c through the Fresnel term
+struct Grads {       // accumulated over lights (without the constant image-gradient factor)
+  T kdp[3];          // dL/d kdp_c
+  T sF[3];           // sum of gfp_c * Q * (1 - sphg)   (co-located: sum of gfp_c * Q; (1-sphg) applied in the epilogue)
   T a2, k;
   T n[3];
-  T pw[3];           // dL/d light_pow_c (only when requested)
+  T pw[3];           // sum of gfp_c * fp_c = pw_c * dL/dpw_c (only when requested)
   T loss;            // sum of squared differences (L2 modes)
 };
 
-// Texel centre: ((j + 0.5)/W_full - 0.5) * size in the reference's fp32 op order
+// Texel centre: ((j + 0.5)/res - 0.5) * size in the reference's fp32 op order
 // (microfacet.py:16-19; y is negated, rows index y).
 template <typename T>
 SV_HD void texel_position(int row, int col, int res, float size, T& px, T& py) {
@@ -174,7 +181,7 @@ SV_HD void texel_position(int row, int col, int res, float size, T& px, T& py) {
 // Prologue: 9 channels -> material parameters.  `t` must already be clamped to [-1,1]
 // by the caller when the outer clamp of svbrdf.py:60 applies.
 template <typename T>
-SV_HD void texel_prologue(const T t[9], Texel<T>& tx, TexelAux<T>& ax) {
+SV_HD void texel_prologue(const T t[9], const T pw[3], Texel<T>& tx, TexelAux<T>& ax) {
   const T inv_pi = T(1.0 / kPi);
   T r;
   T x;
@@ -183,9 +190,13 @@ SV_HD void texel_prologue(const T t[9], Texel<T>& tx, TexelAux<T>& ax) {
     ax.d[c] = pow22(x, r);
     ax.dpow[c] = T(0.5 * kGamma) * x * r;
     x = (t[6 + c] + T(1)) * T(0.5);
-    tx.s[c] = pow22(x, r);
+    const T s = pow22(x, r);
     ax.dpow[4 + c] = T(0.5 * kGamma) * x * r;
-    tx.kd[c] = ax.d[c] * inv_pi * (T(1) - tx.s[c]);
+    ax.oms[c] = T(1) - s;
+    tx.kdp[c] = pw[c] * (ax.d[c] * inv_pi * ax.oms[c]);
+    tx.sp[c] = pw[c] * s;
+    tx.omsp[c] = pw[c] * ax.oms[c];
+    tx.Fp[c] = Fm<T>::fma(tx.omsp[c], T(kSphgColoc), tx.sp[c]);
   }
   x = (t[5] + T(1)) * T(0.5);
   ax.rough = pow22(x, r);
@@ -212,7 +223,7 @@ SV_HD void texel_prologue(const T t[9], Texel<T>& tx, TexelAux<T>& ax) {
 
 template <typename T>
 SV_HD void grads_zero(Grads<T>& g) {
-  for (int c = 0; c < 3; ++c) g.kd[c] = g.sF[c] = g.n[c] = g.pw[c] = T(0);
+  for (int c = 0; c < 3; ++c) g.kdp[c] = g.sF[c] = g.n[c] = g.pw[c] = T(0);
   g.a2 = g.k = g.loss = T(0);
 }
 
@@ -231,42 +242,107 @@ struct LightGeom {   // per light, texture independent
   T lx, ly, lz, lz2; // light position, lz^2 (unused when co-located)
 };
 
-template <typename T, int MODE, bool COLOC, bool WANT_POW>
-SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T pw[3], const T io[3], T out[3], Grads<T>& g) {
+// Radiance -> clamp -> gamma for the 3 channels, and the image gradient gI_c (without its
+// constant factor) in the gradient modes.  fp_c = pw_c * f_c, w = n.l / d^2.
+template <typename T, int MODE, bool WANT_POW>
+SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out[3], Grads<T>& g, T& gw, T& gQ) {
   typedef Fm<T> F;
-  // --- geometry (microfacet.py:91-99) ---
+  gw = T(0);
+  gQ = T(0);
+  for (int c = 0; c < 3; ++c) {
+    const T I = fp[c] * w;                                    // microfacet.py:117
+    const T Icl = F::min(F::max(I, T(kEps)), T(1));           // microfacet.py:120
+    const T lg = F::lg2(Icl);
+    if (MODE == kRender) {
+      out[c] = F::ex2(lg * T(1.0 / kGamma));
+      continue;
+    }
+    T up;
+    if (MODE == kL2) {
+      const T diff = F::ex2(lg * T(1.0 / kGamma)) - io[c];
+      g.loss = F::fma(diff, diff, g.loss);
+      up = diff;
+    } else {
+      up = io[c];
+    }
+    // d out/d I = (1/gamma) Icl^(1/gamma - 1), zero outside the clamp (inclusive edges)
+    const T slope = F::ex2(lg * T(1.0 / kGamma - 1.0));
+    const T gI = (I == Icl) ? up * slope : T(0);
+    const T gfp = gI * w;                                     // dL/d fp_c
+    g.kdp[c] += gfp;
+    gw = F::fma(gI, fp[c], gw);
+    gQ = F::fma(gfp, Fp[c], gQ);
+    if (WANT_POW) g.pw[c] = F::fma(gfp, fp[c], g.pw[c]);
+    out[c] = gfp;                                             // handed back for the Fresnel-albedo gradient
+  }
+}
+
+// Co-located light and camera (everything the reference's capture emits): l = v = h, v.h = 1,
+// n.v = n.l = n.h = c.  The specular lobe collapses to a function of c alone,
+//     Q = D G / q = a2 c^2 / (Dd gv^2 q),   Dd = pi den^2 + eps, den = c2 a2 + 1 - c2,
+//     gv = c (1-k) + k,  q = 4 c^2 + eps,
+// and its gradient is taken through d ln Q.
+template <typename T, int MODE, bool WANT_POW>
+SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
+  typedef Fm<T> F;
   const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
   const T vv = F::fma(Vx, Vx, F::fma(Vy, Vy, lg.cz2));
   const T rv = rsqrt_dir(vv);
-  const T nV = F::fma(tx.n[0], Vx, F::fma(tx.n[1], Vy, tx.n[2] * Vz));
-  const T ndv_raw = nV * rv;
-  T Lx, Ly, Lz, rl, ndl_raw, ndh_raw, vdh, rh, inv_d2;
-  if (COLOC) {
-    // light == camera: l = v = h, v.h = 1
-    Lx = Vx; Ly = Vy; Lz = Vz;
-    rl = rv;
-    ndl_raw = ndv_raw;
-    ndh_raw = ndv_raw;
-    vdh = T(1);
-    rh = T(0.5);
-    inv_d2 = rv * rv;
-  } else {
-    Lx = lg.lx - tx.px; Ly = lg.ly - tx.py; Lz = lg.lz;
-    const T d2 = F::fma(Lx, Lx, F::fma(Ly, Ly, lg.lz2));
-    rl = rsqrt_dir(d2);
-    inv_d2 = rl * rl;
-    const T nL = F::fma(tx.n[0], Lx, F::fma(tx.n[1], Ly, tx.n[2] * Lz));
-    ndl_raw = nL * rl;
-    const T lv = F::fma(Lx, Vx, F::fma(Ly, Vy, Lz * Vz)) * (rl * rv);
-    const T opl = T(1) + lv;               // |l+v|^2 / 2
-    rh = rsqrt_dir(opl + opl);
-    ndh_raw = (ndl_raw + ndv_raw) * rh;
-    vdh = F::max(opl * rh, T(0));
-  }
+  const T c_raw = F::fma(tx.n[0], Vx, F::fma(tx.n[1], Vy, tx.n[2] * Vz)) * rv;
+  const T c = F::max(c_raw, T(0));
+  const T inv_d2 = rv * rv;
+  const T w = c * inv_d2;
+  const T c2 = c * c;
+  const T den = F::fma(c2, tx.a2, T(1) - c2);
+  const T Dd = F::fma(T(kPi) * den, den, T(kEps));
+  const T gv = F::fma(c, tx.omk, tx.k);
+  const T q = F::fma(c2, T(4), T(kEps));
+  const T rDd = F::rcp(Dd), rgv = F::rcp(gv), rq = F::rcp(q);
+  const T Rc = c * rDd * (rgv * rgv) * rq;                    // Q / (a2 c)
+  const T R0 = Rc * c;                                        // Q / a2
+  const T Q = tx.a2 * R0;
+  T fp[3], gfp[3], gw, gQ;
+  for (int ch = 0; ch < 3; ++ch) fp[ch] = F::fma(Q, tx.Fp[ch], tx.kdp[ch]);
+  channels<T, MODE, WANT_POW>(fp, tx.Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ);
+  if (MODE == kRender) return;
+
+  for (int ch = 0; ch < 3; ++ch) g.sF[ch] = F::fma(gfp[ch], Q, g.sF[ch]);
+  const T Tq = gQ * Q;
+  const T u = rDd * (T(2.0 * kPi) * den);                     // (dDd/dden)/Dd
+  g.a2 = F::fma(gQ, R0, F::fma(-(Tq * u), c2, g.a2));         // dQ/da2 = Q/a2 - Q u c2
+  const T m2T = T(-2) * Tq;
+  g.k = F::fma(m2T * (T(1) - c), rgv, g.k);                   // dQ/dk  = -2 Q (1-c)/gv
+  // dQ/dc = 2 Q/c - 2 Q [ c (u (a2-1) + 4/q) + (1-k)/gv ];  w = c/d2
+  const T s1 = F::fma(u, tx.a2 - T(1), T(4) * rq);
+  const T S = F::fma(c, s1, tx.omk * rgv);
+  const T gc = F::fma(gQ + gQ, tx.a2 * Rc, F::fma(m2T, S, gw * inv_d2));
+  // clamp(min=0): below the horizon c = 0 -> I = 0 -> clamped to eps -> gI = 0 -> gc = 0 already
+  const T cV = gc * rv;
+  g.n[0] = F::fma(cV, Vx, g.n[0]);
+  g.n[1] = F::fma(cV, Vy, g.n[1]);
+  g.n[2] = F::fma(cV, Vz, g.n[2]);
+}
+
+// General light/camera pair.
+template <typename T, int MODE, bool WANT_POW>
+SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
+  typedef Fm<T> F;
+  // --- geometry (microfacet.py:91-99) ---
+  const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
+  const T rv = rsqrt_dir(F::fma(Vx, Vx, F::fma(Vy, Vy, lg.cz2)));
+  const T ndv_raw = F::fma(tx.n[0], Vx, F::fma(tx.n[1], Vy, tx.n[2] * Vz)) * rv;
+  const T Lx = lg.lx - tx.px, Ly = lg.ly - tx.py, Lz = lg.lz;
+  const T rl = rsqrt_dir(F::fma(Lx, Lx, F::fma(Ly, Ly, lg.lz2)));
+  const T inv_d2 = rl * rl;
+  const T ndl_raw = F::fma(tx.n[0], Lx, F::fma(tx.n[1], Ly, tx.n[2] * Lz)) * rl;
+  const T lv = F::fma(Lx, Vx, F::fma(Ly, Vy, Lz * Vz)) * (rl * rv);
+  const T opl = T(1) + lv;                                    // |l+v|^2 / 2
+  const T rh = rsqrt_dir(opl + opl);
+  const T ndh_raw = (ndl_raw + ndv_raw) * rh;
+  const T vdh = F::max(opl * rh, T(0));
   const T ndv = F::max(ndv_raw, T(0));
   const T ndl = F::max(ndl_raw, T(0));
   const T ndh = F::max(ndh_raw, T(0));
-
   // --- GGX (microfacet.py:28-32) ---
   const T c2 = ndh * ndh;
   const T den = F::fma(c2, tx.a2, T(1) - c2);
@@ -274,70 +350,27 @@ SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T pw[3]
   const T rDd = F::rcp(Dd);
   const T D = tx.a2 * rDd;
   // --- Fresnel (microfacet.py:43-45) ---
-  T sphg;
-  if (COLOC) {
-    sphg = T(1.6815857857725708e-4);       // 2^(-5.55473 - 6.98316)
-  } else {
-    sphg = F::ex2(F::fma(T(kFresA), vdh, T(kFresB)) * vdh);
-  }
+  const T sphg = F::ex2(F::fma(T(kFresA), vdh, T(kFresB)) * vdh);
   // --- Smith (microfacet.py:47-52) ---
-  const T gv = F::fma(ndv, tx.omk, tx.k);
-  const T gl = COLOC ? gv : F::fma(ndl, tx.omk, tx.k);
-  const T rgv = F::rcp(gv);
-  const T rgl = COLOC ? rgv : F::rcp(gl);
-  const T A = ndv * rgv;
-  const T B = ndl * rgl;
+  const T rgv = F::rcp(F::fma(ndv, tx.omk, tx.k));
+  const T rgl = F::rcp(F::fma(ndl, tx.omk, tx.k));
+  const T A = ndv * rgv, B = ndl * rgl;
   const T G = A * B;
   // --- specular lobe (microfacet.py:109) ---
-  const T q = F::fma(T(4) * ndv, ndl, T(kEps));
-  const T rq = F::rcp(q);
-  const T DGq = D * rq;                    // D/q
+  const T rq = F::rcp(F::fma(T(4) * ndv, ndl, T(kEps)));
+  const T DGq = D * rq;
   const T Q = DGq * G;
-  // --- radiance, clamp, gamma (microfacet.py:112-120) ---
   const T w = ndl * inv_d2;
-  T f[3], I[3], Icl[3], lgI[3];
-  for (int c = 0; c < 3; ++c) {
-    const T Fc = F::fma(T(1) - tx.s[c], sphg, tx.s[c]);
-    f[c] = F::fma(Q, Fc, tx.kd[c]);
-    I[c] = pw[c] * f[c] * w;
-    Icl[c] = F::min(F::max(I[c], T(kEps)), T(1));
-    lgI[c] = F::lg2(Icl[c]);
+  T fp[3], Fp[3], gfp[3], gw, gQ;
+  for (int ch = 0; ch < 3; ++ch) {
+    Fp[ch] = F::fma(tx.omsp[ch], sphg, tx.sp[ch]);
+    fp[ch] = F::fma(Q, Fp[ch], tx.kdp[ch]);
   }
-  if (MODE == kRender) {
-    for (int c = 0; c < 3; ++c) out[c] = F::ex2(lgI[c] * T(1.0 / kGamma));
-    return;
-  }
+  channels<T, MODE, WANT_POW>(fp, Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ);
+  if (MODE == kRender) return;
 
-  // --- image gradient without its constant factor ---
-  T gI[3];
-  for (int c = 0; c < 3; ++c) {
-    T up;
-    if (MODE == kL2) {
-      const T o = F::ex2(lgI[c] * T(1.0 / kGamma));
-      const T diff = o - io[c];
-      g.loss = F::fma(diff, diff, g.loss);
-      up = diff;
-    } else {
-      up = io[c];
-    }
-    // d out / d I = (1/gamma) * Icl^(1/gamma - 1), zero outside the clamp (inclusive edges)
-    const T slope = F::ex2(lgI[c] * T(1.0 / kGamma - 1.0));
-    gI[c] = (I[c] == Icl[c]) ? up * slope : T(0);
-  }
-
-  // --- back through the radiance ---
-  T gw = T(0), gQ = T(0);
-  const T oms_sphg = T(1) - sphg;
-  for (int c = 0; c < 3; ++c) {
-    const T tc = gI[c] * f[c];
-    gw = F::fma(tc, pw[c], gw);
-    if (WANT_POW) g.pw[c] = F::fma(tc, w, g.pw[c]);
-    const T gf = gI[c] * pw[c] * w;
-    g.kd[c] += gf;
-    const T Fc = F::fma(T(1) - tx.s[c], sphg, tx.s[c]);
-    gQ = F::fma(gf, Fc, gQ);
-    g.sF[c] = F::fma(gf * Q, oms_sphg, g.sF[c]);
-  }
+  const T QomS = Q * (T(1) - sphg);
+  for (int ch = 0; ch < 3; ++ch) g.sF[ch] = F::fma(gfp[ch], QomS, g.sF[ch]);
   // Q = D*G/q
   const T gD = gQ * G * rq;
   const T gG = gQ * DGq;
@@ -356,18 +389,17 @@ SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T pw[3]
   const T mv = (ndv_raw >= T(0)) ? gndv : T(0);
   const T ml = (ndl_raw >= T(0)) ? gndl : T(0);
   const T mh = (ndh_raw >= T(0)) ? gndh * rh : T(0);
-  if (COLOC) {
-    const T cV = (mv + ml + mh + mh) * rv;
-    g.n[0] = F::fma(cV, Vx, g.n[0]);
-    g.n[1] = F::fma(cV, Vy, g.n[1]);
-    g.n[2] = F::fma(cV, Vz, g.n[2]);
-  } else {
-    const T cV = (mv + mh) * rv;
-    const T cL = (ml + mh) * rl;
-    g.n[0] = F::fma(cV, Vx, F::fma(cL, Lx, g.n[0]));
-    g.n[1] = F::fma(cV, Vy, F::fma(cL, Ly, g.n[1]));
-    g.n[2] = F::fma(cV, Vz, F::fma(cL, Lz, g.n[2]));
-  }
+  const T cV = (mv + mh) * rv;
+  const T cL = (ml + mh) * rl;
+  g.n[0] = F::fma(cV, Vx, F::fma(cL, Lx, g.n[0]));
+  g.n[1] = F::fma(cV, Vy, F::fma(cL, Ly, g.n[1]));
+  g.n[2] = F::fma(cV, Vz, F::fma(cL, Lz, g.n[2]));
+}
+
+template <typename T, int MODE, bool COLOC, bool WANT_POW>
+SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
+  if (COLOC) shade_light_coloc<T, MODE, WANT_POW>(tx, lg, io, out, g);
+  else shade_light_general<T, MODE, WANT_POW>(tx, lg, io, out, g);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,13 +408,16 @@ SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T pw[3]
 // `outer` = mask of the caller's clamp(-1,1) on the raw parameter (svbrdf.py:60); pass all-true
 // when the clamp belongs to the caller's graph (mode B).
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const Grads<T>& g, T scale, const bool outer[9], T gt[9]) {
+template <typename T, bool COLOC>
+SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[3], const Grads<T>& g, T scale, const bool outer[9],
+                          T gt[9]) {
   typedef Fm<T> F;
   const T inv_pi = T(1.0 / kPi);
+  const T sf = COLOC ? T(1.0 - kSphgColoc) : T(1);
   for (int c = 0; c < 3; ++c) {
-    const T gd = g.kd[c] * (T(1) - tx.s[c]) * inv_pi;
-    const T gs = F::fma(-g.kd[c], ax.d[c] * inv_pi, g.sF[c]);
+    const T gkd = g.kdp[c] * pw[c];                           // dL/d (d_c/pi (1-s_c))
+    const T gd = gkd * ax.oms[c] * inv_pi;
+    const T gs = F::fma(-gkd, ax.d[c] * inv_pi, g.sF[c] * (pw[c] * sf));
     gt[c] = gd * ax.dpow[c];
     gt[6 + c] = gs * ax.dpow[4 + c];
   }
@@ -400,6 +435,10 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const Grads
   gt[4] = ax.in4 ? F::fma(gplanar, ax.my + ax.my, gmy) : T(0);
   for (int kk = 0; kk < 9; ++kk) gt[kk] = outer[kk] ? gt[kk] * scale : T(0);
 }
+
+// dL/d light_pow_c from the accumulated sum of gfp_c * fp_c (= pw_c * dL/dpw_c).
+template <typename T>
+SV_HD T pow_grad(T acc, T pw) { return pw != T(0) ? acc / pw : T(0); }
 
 // ---------------------------------------------------------------------------------------------
 // Adam (torch/optim/adam.py:531-547, single-tensor path, amsgrad off, weight decay 0).

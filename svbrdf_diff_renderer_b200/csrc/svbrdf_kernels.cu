@@ -1,18 +1,31 @@
 // sm_100a kernels + C ABI (include/svbrdf_b200.h) of the per-pixel SVBRDF optimisation path.
 //
-// One thread owns one texel for the whole pass: it loads the texel's 9 channels once
-// (coalesced: a warp reads 128 contiguous bytes of each plane), keeps the material
-// parameters and the gradient accumulators in registers, loops over all lights, and
-// finishes with the texture-gradient epilogue and — in the fused mode — the Adam update.
-// The rendered image is never written in the L2 modes; nothing image-sized is saved
-// between forward and backward (the backward kernel recomputes the forward per light).
-//
-// Per-light geometry (2 x float4 per light) is staged in shared memory once per CTA and
-// read with broadcast LDS.128.  Whether every light is co-located with its camera is
-// detected while staging; co-located captures (everything the reference's capture code
-// emits, capture.py:70-71) take a loop body with l = v = h folded.
-//
+// One thread owns one texel for the whole pass: the texel's 9 channels are read once, the
+// material parameters and gradient accumulators stay in registers while the thread loops over
+// all lights, and the pass ends with the texture-gradient epilogue and — in the fused mode —
+// the Adam update.  The rendered image is never written in the L2 modes and nothing image-sized
+// is saved between forward and backward (the backward kernel recomputes the forward per light).
 // The arithmetic is elementwise and transcendental (MUFU) bound: no tensor cores.
+//
+// Two kernels implement that pass:
+//
+//  * tile_kernel  (the hot path) — persistent, warp-specialised.  Each CTA walks over 256-texel
+//    tiles.  A producer warp streams every byte the tile needs (texture planes, 3 lights of
+//    targets per chunk, Adam m and v) from HBM into a shared-memory ring with 1-D TMA bulk copies
+//    (cp.async.bulk ... mbarrier::complete_tx); eight consumer warps wait on the slot's mbarrier,
+//    pull their texel's values with conflict-free LDS, release the slot and compute.  The ring
+//    keeps up to kSlots x 9 KB per CTA in flight without costing the consumers a single register,
+//    which is what the first version of this kernel (plain LDG with a 2-light register prefetch)
+//    could not do: ncu showed 6.8 warps per issue slot stalled on long-scoreboard at 24 %
+//    occupancy (profiles/r01_v1_ldg_*.txt).  Results leave through coalesced STG.
+//
+//  * texel_kernel — one thread per texel with direct LDG/STG.  Used for the forward render
+//    (store-dominated: nothing to stage) and as the general fallback whenever the TMA alignment
+//    rules (16-byte aligned plane segments) do not hold.
+//
+// Per-light geometry (2 x float4 per light) is staged in shared memory once per CTA.  Whether
+// every light is co-located with its camera is detected while staging; co-located captures
+// (everything the reference's capture code emits, capture.py:70-71) take the folded loop body.
 #include <cuda_runtime.h>
 
 #include "../../include/svbrdf_b200.h"
@@ -20,8 +33,11 @@
 
 namespace svbrdf {
 
-constexpr int kThreads = 256;
-constexpr int kPrefetch = 2;   // lights of target/grad_out data in flight per thread
+constexpr int kThreads = 256;          // texels per tile == consumer threads per CTA
+constexpr int kPrefetch = 2;           // texel_kernel: lights of io data in flight per thread
+constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
+constexpr int kSlotPlanes = 9;         // planes per ring slot (9 texture channels, or 3 lights x 3)
+constexpr int kConsumerWarps = kThreads / 32;
 
 enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3 };
 
@@ -31,10 +47,10 @@ struct Params {
   float* v;              // Adam second moment (kModeL2Adam)
   const float* cam;      // [N,3]
   const float* light;    // [N,3]
-  const float* pow;      // [3]
+  float* pow;            // [3] (updated in place by the fused optim_light path)
   const void* io;        // target (L2 modes) or grad_out (VJP): [N,3] planes
   float* out;            // rendered image [N,3] planes (render) or grad_tex [9] planes
-  float* partials;       // [gridDim.x][4]: loss, gpow[3]
+  float* partials;       // [blocks][4]: loss, gpow[3]; then the finish counter
   long long stride;      // plane stride in elements
   long long texels;      // rows * res
   float size;
@@ -43,43 +59,145 @@ struct Params {
   int n_lights;
   float scale;           // constant image-gradient factor
   AdamStep<float> adam;
+  // finalisation by the last CTA to finish (tile_kernel)
+  double loss_norm;      // 1/(n_total*3*res*res)
+  float* loss_out;       // nullable
+  float* grad_pow;       // nullable [3]
+  float* pow_state;      // nullable: Adam m[3], v[3] of light_pow (optim_light)
+  unsigned int* counter; // finish counter (zero before and after every launch)
+  int slots;             // ring depth
 };
 
 template <int TGT>
 struct IoLoad;
 template <>
 struct IoLoad<SVBRDF_TARGET_F32> {
-  static __device__ __forceinline__ float at(const void* base, long long idx) {
-    return __ldg(static_cast<const float*>(base) + idx);
-  }
+  typedef float elem;
+  static __device__ __forceinline__ float decode(float x) { return x; }
 };
 template <>
 struct IoLoad<SVBRDF_TARGET_U8> {
+  typedef unsigned char elem;
   // float(b)/255 correctly rounded (bit-identical to the IEEE division of imageio.py:18-19):
   // q = b*r, one Newton correction with the exact residual.
-  static __device__ __forceinline__ float at(const void* base, long long idx) {
-    const float b = float(__ldg(static_cast<const unsigned char*>(base) + idx));
+  static __device__ __forceinline__ float decode(unsigned char x) {
+    const float b = float(x);
     const float r = 1.0f / 255.0f;
     const float q = b * r;
     return __fmaf_rn(__fmaf_rn(-q, 255.0f, b), r, q);
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool stage_lights(const Params& P, float4* s_geo, int tid, int nthreads) {
+  int same = 1;
+  for (int i = tid; i < P.n_lights; i += nthreads) {
+    const float cx = P.cam[3 * i], cy = P.cam[3 * i + 1], cz = P.cam[3 * i + 2];
+    const float lx = P.light[3 * i], ly = P.light[3 * i + 1], lz = P.light[3 * i + 2];
+    s_geo[2 * i] = make_float4(cx, cy, cz, cz * cz);
+    s_geo[2 * i + 1] = make_float4(lx, ly, lz, lz * lz);
+    same &= (cx == lx) & (cy == ly) & (cz == lz);
+  }
+  return __syncthreads_and(same) != 0;
+}
+
+template <bool COLOC>
+__device__ __forceinline__ LightGeom<float> load_geom(const float4* __restrict__ s_geo, int i) {
+  LightGeom<float> lg;
+  const float4 a = s_geo[2 * i];
+  lg.cx = a.x; lg.cy = a.y; lg.cz = a.z; lg.cz2 = a.w;
+  if (!COLOC) {
+    const float4 b = s_geo[2 * i + 1];
+    lg.lx = b.x; lg.ly = b.y; lg.lz = b.z; lg.lz2 = b.w;
+  }
+  return lg;
+}
+
+template <int MODE>
+__device__ __forceinline__ void clamp_outer(const float raw[9], float t[9], bool outer[9]) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (MODE == kModeL2Grad || MODE == kModeL2Adam) {   // the clamp of svbrdf.py:60
+      outer[k] = raw[k] >= -1.f && raw[k] <= 1.f;
+      t[k] = fminf(fmaxf(raw[k], -1.f), 1.f);
+    } else {
+      outer[k] = true;
+      t[k] = raw[k];
+    }
+  }
+}
+
+// Sums [n][4] partials in double in a fixed order (run-to-run deterministic), writes the loss and
+// the light-power gradient, and — for optim_light — applies Adam to light_pow[3].
+// Every thread of the CTA must call it (it synchronises); threads with tid >= 256 only synchronise.
+__device__ __forceinline__ void finalize_block(const Params& P, int n, double (*s)[4], int tid) {
+  if (tid < 256) {
+    double acc[4] = {0, 0, 0, 0};
+    for (int b = tid; b < n; b += 256) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(P.partials) + b);
+      acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[tid][c] = acc[c];
+  }
+  __syncthreads();
+  double tot = 0;
+  if (tid < 4) {
+    for (int i = 0; i < 256; ++i) tot += s[i][tid];
+  }
+  __syncthreads();
+  if (tid < 4) s[0][tid] = tot;
+  __syncthreads();
+  if (tid == 0 && P.loss_out) P.loss_out[0] = float(s[0][0] * P.loss_norm);
+  if (tid < 3 && (P.grad_pow || P.pow_state)) {
+    const float pw = P.pow[tid];
+    const float gp = pow_grad(float(s[0][1 + tid] * double(P.scale)), pw);
+    if (P.grad_pow) P.grad_pow[tid] = gp;
+    if (P.pow_state) {
+      float p = pw, m = P.pow_state[tid], v = P.pow_state[3 + tid];
+      // 3 elements: IEEE sqrt/div, cost is nil (adam.py:531-547)
+      m = m + (gp - m) * P.adam.one_minus_b1;
+      v = v * P.adam.b2 + P.adam.one_minus_b2 * gp * gp;
+      const float denom = sqrtf(v) * P.adam.inv_sqrt_bc2 + P.adam.eps;
+      p = p - P.adam.step_size * m / denom;
+      P.pow[tid] = p;
+      P.pow_state[tid] = m;
+      P.pow_state[3 + tid] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_reduce4(float r[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// texel_kernel: one thread per texel, direct LDG/STG
+// ---------------------------------------------------------------------------------------------
 template <int MODE, bool COLOC, bool WANT_POW, int TGT>
-__device__ __forceinline__ void light_loop(const Params& P, const float4* __restrict__ s_geo, const Texel<float>& tx,
-                                            const float pw[3], long long p, bool valid, Grads<float>& g) {
+__device__ __forceinline__ void light_loop(const Params& P, const float4* __restrict__ s_geo, const Texel<float>& tx, long long p,
+                                            bool valid, Grads<float>& g) {
+  typedef typename IoLoad<TGT>::elem elem;
   const int N = P.n_lights;
-  const long long stride = P.stride;
   constexpr int LM = (MODE == kModeRender) ? kRender : (MODE == kModeVjp ? kVjp : kL2);
+  const long long step = 3 * P.stride;
+  const elem* __restrict__ src = static_cast<const elem*>(P.io) + p;    // light 0, channel 0
+  float* __restrict__ dst = P.out + p;
 
   float buf[kPrefetch][3];
   if (MODE != kModeRender) {
 #pragma unroll
     for (int j = 0; j < kPrefetch; ++j) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        buf[j][c] = (valid && j < N) ? IoLoad<TGT>::at(P.io, (long long)(j * 3 + c) * stride + p) : 0.f;
+      for (int c = 0; c < 3; ++c) buf[j][c] = (valid && j < N) ? IoLoad<TGT>::decode(__ldg(src + j * step + c * P.stride)) : 0.f;
     }
+    src += kPrefetch * step;
   }
   for (int i0 = 0; i0 < N; i0 += kPrefetch) {
 #pragma unroll
@@ -90,23 +208,20 @@ __device__ __forceinline__ void light_loop(const Params& P, const float4* __rest
       if (MODE != kModeRender) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) in3[c] = buf[j][c];
-        const int nx = i + kPrefetch;
-        if (nx < N && valid) {
+        if (i + kPrefetch < N && valid) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) buf[j][c] = IoLoad<TGT>::at(P.io, ((long long)nx * 3 + c) * stride + p);
+          for (int c = 0; c < 3; ++c) buf[j][c] = IoLoad<TGT>::decode(__ldg(src + c * P.stride));
         }
+        src += step;
       }
-      LightGeom<float> lg;
-      const float4 a = s_geo[2 * i];
-      lg.cx = a.x; lg.cy = a.y; lg.cz = a.z; lg.cz2 = a.w;
-      if (!COLOC) {
-        const float4 b = s_geo[2 * i + 1];
-        lg.lx = b.x; lg.ly = b.y; lg.lz = b.z; lg.lz2 = b.w;
-      }
-      shade_light<float, LM, COLOC, WANT_POW>(tx, lg, pw, in3, o3, g);
-      if (MODE == kModeRender && valid) {
+      const LightGeom<float> lg = load_geom<COLOC>(s_geo, i);
+      shade_light<float, LM, COLOC, WANT_POW>(tx, lg, in3, o3, g);
+      if (MODE == kModeRender) {
+        if (valid) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) P.out[((long long)i * 3 + c) * stride + p] = o3[c];
+          for (int c = 0; c < 3; ++c) dst[c * P.stride] = o3[c];
+        }
+        dst += step;
       }
     }
   }
@@ -116,17 +231,7 @@ template <int MODE, bool WANT_POW, int TGT>
 __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
   extern __shared__ float4 s_geo[];
   __shared__ float s_red[kThreads / 32][4];
-
-  // ---- stage per-light geometry, detect co-location ----
-  int same = 1;
-  for (int i = threadIdx.x; i < P.n_lights; i += kThreads) {
-    const float cx = P.cam[3 * i], cy = P.cam[3 * i + 1], cz = P.cam[3 * i + 2];
-    const float lx = P.light[3 * i], ly = P.light[3 * i + 1], lz = P.light[3 * i + 2];
-    s_geo[2 * i] = make_float4(cx, cy, cz, cz * cz);
-    s_geo[2 * i + 1] = make_float4(lx, ly, lz, lz * lz);
-    same &= (cx == lx) & (cy == ly) & (cz == lz);
-  }
-  const bool coloc = __syncthreads_and(same) != 0;
+  const bool coloc = stage_lights(P, s_geo, threadIdx.x, kThreads);
 
   const long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
   const bool valid = p < P.texels;
@@ -134,22 +239,13 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
 
   float pw[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) pw[c] = __ldg(P.pow + c);
+  for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
 
-  // ---- texel prologue ----
   float raw[9], t[9];
   bool outer[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    raw[k] = (MODE == kModeL2Adam) ? P.tex[k * P.stride + pc] : __ldg(P.tex + k * P.stride + pc);
-    if (MODE == kModeL2Grad || MODE == kModeL2Adam) {   // the clamp of svbrdf.py:60
-      outer[k] = raw[k] >= -1.f && raw[k] <= 1.f;
-      t[k] = fminf(fmaxf(raw[k], -1.f), 1.f);
-    } else {
-      outer[k] = true;
-      t[k] = raw[k];
-    }
-  }
+  for (int k = 0; k < 9; ++k) raw[k] = (MODE == kModeL2Adam) ? P.tex[k * P.stride + pc] : __ldg(P.tex + k * P.stride + pc);
+  clamp_outer<MODE>(raw, t, outer);
   Texel<float> tx;
   TexelAux<float> ax;
   {
@@ -157,18 +253,17 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
     const int col = int(pc - (long long)row * P.res);
     texel_position(row + P.row_offset, col, P.res, P.size, tx.px, tx.py);
   }
-  texel_prologue(t, tx, ax);
+  texel_prologue(t, pw, tx, ax);
   Grads<float> g;
   grads_zero(g);
 
-  // ---- all lights ----
-  if (coloc) light_loop<MODE, true, WANT_POW, TGT>(P, s_geo, tx, pw, pc, valid, g);
-  else light_loop<MODE, false, WANT_POW, TGT>(P, s_geo, tx, pw, pc, valid, g);
+  if (coloc) light_loop<MODE, true, WANT_POW, TGT>(P, s_geo, tx, pc, valid, g);
+  else light_loop<MODE, false, WANT_POW, TGT>(P, s_geo, tx, pc, valid, g);
   if (MODE == kModeRender) return;
 
-  // ---- epilogue ----
   float gt[9];
-  texel_epilogue(tx, ax, g, P.scale, outer, gt);
+  if (coloc) texel_epilogue<float, true>(tx, ax, pw, g, P.scale, outer, gt);
+  else texel_epilogue<float, false>(tx, ax, pw, g, P.scale, outer, gt);
   if (valid) {
     if (MODE == kModeL2Adam) {
 #pragma unroll
@@ -186,17 +281,11 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
     }
   }
 
-  // ---- block partials: loss and light-power gradient (fixed order => deterministic) ----
+  // block partials: loss and light-power gradient (fixed order => deterministic)
   constexpr bool kHasLoss = (MODE == kModeL2Grad || MODE == kModeL2Adam);
   if (kHasLoss || WANT_POW) {
     float r[4] = {valid ? g.loss : 0.f, valid ? g.pw[0] : 0.f, valid ? g.pw[1] : 0.f, valid ? g.pw[2] : 0.f};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c == 0 ? kHasLoss : WANT_POW) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
-      }
-    }
+    warp_reduce4(r);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
 #pragma unroll
@@ -212,49 +301,273 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
   }
 }
 
-// Sums the block partials in double (fixed tree => run-to-run deterministic), writes the loss
-// and the light-power gradient, and — for optim_light — applies Adam to light_pow[3].
-struct FinalizeParams {
-  const float* partials;
-  int n_blocks;
-  double loss_norm;       // 1/(n_total*3*res*res)
-  float grad_scale;       // constant image-gradient factor for gpow
-  float* loss_out;        // nullable
-  float* grad_pow;        // nullable [3]
-  float* pow;             // nullable: light_pow to update (optim_light)
-  float* pow_state;       // m[3], v[3]
-  AdamStep<float> adam;
-};
-
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams F) {
+// Finalisation for texel_kernel launches (one small CTA).
+__global__ void __launch_bounds__(256) finalize_kernel(const Params P, int n_blocks) {
   __shared__ double s[256][4];
-  double acc[4] = {0, 0, 0, 0};
-  for (int b = threadIdx.x; b < F.n_blocks; b += 256) {
-    const float4 q = reinterpret_cast<const float4*>(F.partials)[b];
-    acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+  finalize_block(P, n_blocks, s, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_kernel: persistent CTAs, TMA bulk copies into a shared-memory ring, mbarrier pipeline
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
   }
-  for (int c = 0; c < 4; ++c) s[threadIdx.x][c] = acc[c];
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w)
-      for (int c = 0; c < 4; ++c) s[threadIdx.x][c] += s[threadIdx.x + w][c];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && F.loss_out) F.loss_out[0] = float(s[0][0] * F.loss_norm);
-  if (threadIdx.x < 3) {
-    const float gp = float(s[0][1 + threadIdx.x] * double(F.grad_scale));
-    if (F.grad_pow) F.grad_pow[threadIdx.x] = gp;
-    if (F.pow) {
-      float p = F.pow[threadIdx.x], m = F.pow_state[threadIdx.x], v = F.pow_state[3 + threadIdx.x];
-      // light_pow has 3 elements: IEEE sqrt/div here, cost is nil
-      m = m + (gp - m) * F.adam.one_minus_b1;
-      v = v * F.adam.b2 + F.adam.one_minus_b2 * gp * gp;
-      const float denom = sqrtf(v) * F.adam.inv_sqrt_bc2 + F.adam.eps;
-      p = p - F.adam.step_size * m / denom;
-      F.pow[threadIdx.x] = p;
-      F.pow_state[threadIdx.x] = m;
-      F.pow_state[3 + threadIdx.x] = v;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0,
+// both addresses 16-byte aligned).
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kSlotBytes = kSlotPlanes * kThreads * 4;     // 9216
+
+// Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
+template <int MODE>
+__device__ __forceinline__ int chunks_per_tile(int n_lights) {
+  return 1 + (n_lights + kChunkLights - 1) / kChunkLights + (MODE == kModeL2Adam ? 2 : 0);
+}
+
+template <int MODE, bool COLOC, bool WANT_POW, int TGT>
+__device__ __forceinline__ void tile_consumer(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
+                                               unsigned long long* full, unsigned long long* empty, float loss_acc[4]) {
+  typedef typename IoLoad<TGT>::elem elem;
+  constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = P.n_lights, S = P.slots;
+  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  float pw[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
+
+  unsigned it = 0;        // running chunk index of this CTA
+  unsigned slot = 0, phase = 0;
+  auto advance = [&]() { ++it; if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p = tile * kThreads + tid;
+    const bool valid = p < P.texels;
+
+    // ---- texel prologue ----
+    float raw[9], t[9];
+    bool outer[9];
+    mbar_wait(&full[slot], phase);
+    {
+      const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = s[k * kThreads + tid];
     }
+    release(slot);
+    advance();
+    if (!valid) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = 0.f;
+    }
+    clamp_outer<MODE>(raw, t, outer);
+    Texel<float> tx;
+    TexelAux<float> ax;
+    {
+      const long long pc = valid ? p : 0;
+      int row, col;
+      if (P.texels < (1ll << 32)) {
+        row = int(unsigned(pc) / unsigned(P.res));
+        col = int(unsigned(pc) - unsigned(row) * unsigned(P.res));
+      } else {
+        row = int(pc / P.res);
+        col = int(pc - (long long)row * P.res);
+      }
+      texel_position(row + P.row_offset, col, P.res, P.size, tx.px, tx.py);
+    }
+    texel_prologue(t, pw, tx, ax);
+    Grads<float> g;
+    grads_zero(g);
+
+    // ---- lights, 3 per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+      float in[kChunkLights][3];
+      mbar_wait(&full[slot], phase);
+      {
+        const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * kSlotBytes);
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kThreads + tid]) : 0.f;
+        }
+      }
+      release(slot);
+      advance();
+#pragma unroll
+      for (int j = 0; j < kChunkLights; ++j) {
+        if (i0 + j < N) {
+          float o3[3];
+          const LightGeom<float> lg = load_geom<COLOC>(s_geo, i0 + j);
+          shade_light<float, LM, COLOC, WANT_POW>(tx, lg, in[j], o3, g);
+        }
+      }
+    }
+
+    // ---- epilogue ----
+    float gt[9];
+    texel_epilogue<float, COLOC>(tx, ax, pw, g, P.scale, outer, gt);
+    if (MODE == kModeL2Adam) {
+      float mk[9], vk[9];
+      mbar_wait(&full[slot], phase);
+      {
+        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mk[k] = s[k * kThreads + tid];
+      }
+      release(slot);
+      advance();
+      mbar_wait(&full[slot], phase);
+      {
+        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vk[k] = s[k * kThreads + tid];
+      }
+      release(slot);
+      advance();
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const long long idx = k * P.stride + p;
+          float pk = raw[k];
+          adam_update(pk, mk[k], vk[k], gt[k], P.adam);
+          P.tex[idx] = pk;
+          P.m[idx] = mk[k];
+          P.v[idx] = vk[k];
+        }
+      }
+    } else if (valid) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) P.out[k * P.stride + p] = gt[k];
+    }
+    if (valid) {
+      loss_acc[0] += g.loss;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c];
+    }
+  }
+}
+
+template <int MODE, int TGT>
+__device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ring, unsigned long long* full, unsigned long long* empty) {
+  typedef typename IoLoad<TGT>::elem elem;
+  const int N = P.n_lights, S = P.slots;
+  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  unsigned slot = 0, phase = 0;
+  auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p0 = tile * kThreads;
+    const unsigned len = unsigned(min((long long)kThreads, P.texels - p0));      // texels in this tile (multiple of 4)
+    auto fill = [&](const void* base, size_t elem_bytes, int planes) {
+      // `planes` plane segments of `len` elements each, starting at element p0 of consecutive planes of `base`
+      mbar_wait(&empty[slot], phase ^ 1);
+      unsigned char* dst = ring + size_t(slot) * kSlotBytes;
+      const unsigned seg = len * unsigned(elem_bytes);
+      mbar_expect_tx(&full[slot], seg * planes);
+      for (int j = 0; j < planes; ++j)
+        tma_load_1d(dst + size_t(j) * kThreads * elem_bytes, static_cast<const unsigned char*>(base) + (size_t(j) * P.stride + p0) * elem_bytes,
+                    seg, &full[slot]);
+      advance();
+    };
+    fill(P.tex, 4, 9);
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+      const int nl = min(kChunkLights, N - i0);
+      fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
+    }
+    if (MODE == kModeL2Adam) {
+      fill(P.m, 4, 9);
+      fill(P.v, 4, 9);
+    }
+  }
+}
+
+template <int MODE, bool WANT_POW, int TGT>
+__global__ void __maxnreg__(112) tile_kernel(const Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: ring [slots * 9216] | barriers full[slots], empty[slots] | light geometry 2*N float4 | reduction scratch
+  unsigned char* ring = smem;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots) * kSlotBytes);
+  unsigned long long* empty = full + P.slots;
+  float4* s_geo = reinterpret_cast<float4*>(empty + P.slots);
+  __shared__ float s_red[kConsumerWarps][4];
+  __shared__ double s_fin[kThreads][4];
+  __shared__ bool s_last;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < P.slots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  const bool coloc = stage_lights(P, s_geo, tid, kThreads + 32);     // includes __syncthreads
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (tid >= kThreads) {
+    if (tid == kThreads) tile_producer<MODE, TGT>(P, ring, full, empty);
+  } else {
+    if (coloc) tile_consumer<MODE, true, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
+    else tile_consumer<MODE, false, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
+  }
+
+  // ---- CTA partial -> global; the last CTA to finish reduces all partials (fixed order) ----
+  if (tid < kThreads) {
+    warp_reduce4(acc);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s_red[tid >> 5][c] = acc[c];
+    }
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) a += s_red[w][tid];
+    __stcg(P.partials + (long long)blockIdx.x * 4 + tid, a);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(P.counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    finalize_block(P, int(gridDim.x), s_fin, tid);
+    if (tid == 0) *P.counter = 0u;                         // leave the workspace ready for the next launch
   }
 }
 
@@ -304,7 +617,7 @@ static int check_geom(const svbrdf_geom_t* g) {
   if (!g || !g->camera_pos || !g->light_pos || !g->light_pow) return SVBRDF_E_BADARG;
   if (g->res <= 0 || g->rows <= 0 || g->n_lights <= 0 || g->row_offset < 0) return SVBRDF_E_BADARG;
   if (g->plane_stride != 0 && g->plane_stride < (long long)g->rows * g->res) return SVBRDF_E_BADARG;
-  if (size_t(g->n_lights) * 2 * sizeof(float4) > 200 * 1024) return SVBRDF_E_UNSUPPORTED;
+  if (size_t(g->n_lights) * 2 * sizeof(float4) > 64 * 1024) return SVBRDF_E_UNSUPPORTED;   // 2048 lights per call
   return 0;
 }
 
@@ -312,7 +625,7 @@ static Params base_params(const svbrdf_geom_t* g) {
   Params P{};
   P.cam = g->camera_pos;
   P.light = g->light_pos;
-  P.pow = g->light_pow;
+  P.pow = const_cast<float*>(g->light_pow);
   P.texels = (long long)g->rows * g->res;
   P.stride = g->plane_stride ? g->plane_stride : P.texels;
   P.size = g->size;
@@ -322,26 +635,96 @@ static Params base_params(const svbrdf_geom_t* g) {
   return P;
 }
 
-static inline int n_blocks(const Params& P) { return int((P.texels + kThreads - 1) / kThreads); }
+static inline int texel_blocks(const Params& P) { return int((P.texels + kThreads - 1) / kThreads); }
+
+// Workspace layout: [max(texel blocks, persistent CTAs)][4] floats of partials, then the finish counter.
+static inline size_t partial_rows(long long texels) {
+  const size_t tb = size_t((texels + kThreads - 1) / kThreads);
+  return tb > 4096 ? tb : 4096;
+}
+
+struct Device {
+  int sms = 0;
+  int smem_optin = 0;
+};
+static int device_info(Device* d) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return int(e);
+  if ((e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return int(e);
+  if ((e = cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return int(e);
+  return 0;
+}
 
 template <int MODE, bool WANT_POW, int TGT>
-static int launch(const Params& P, cudaStream_t st) {
+static int launch_texel(const Params& P, cudaStream_t st) {
   const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
   auto kern = texel_kernel<MODE, WANT_POW, TGT>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
   }
-  kern<<<n_blocks(P), kThreads, smem, st>>>(P);
+  kern<<<texel_blocks(P), kThreads, smem, st>>>(P);
+  if (cudaError_t e = cudaGetLastError()) return int(e);
+  constexpr bool kHasLoss = (MODE == kModeL2Grad || MODE == kModeL2Adam);
+  if ((kHasLoss && P.loss_out) || P.grad_pow || P.pow_state) {
+    finalize_kernel<<<1, 256, 0, st>>>(P, texel_blocks(P));
+    return int(cudaGetLastError());
+  }
+  return 0;
+}
+
+// The TMA path needs 16-byte aligned plane segments: base pointers, plane stride and tile length.
+template <int TGT>
+static bool tma_ok(const Params& P) {
+  const size_t eb = sizeof(typename IoLoad<TGT>::elem);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al(P.tex) || !al(P.io) || (P.m && !al(P.m)) || (P.v && !al(P.v))) return false;
+  if ((P.stride * 4) % 16 != 0 || (size_t(P.stride) * eb) % 16 != 0) return false;
+  if ((P.texels * 4) % 16 != 0 || (size_t(P.texels) * eb) % 16 != 0) return false;
+  return true;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+template <int MODE, bool WANT_POW, int TGT>
+static int launch_tile(Params P, cudaStream_t st) {
+  if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  Device d;
+  if (int e = device_info(&d)) return e;
+  const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 2);
+  const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
+  const size_t fixed = geo + 64 + 2 * 8 * 64;                          // barriers (<= 64 slots) + padding
+  const size_t static_smem = 9 * 1024;                                 // s_fin + s_red (static __shared__)
+  const size_t budget = size_t(228 * 1024) / ctas_per_sm - 1024 - static_smem;
+  int slots = env_int("SVBRDF_B200_SLOTS", 0);
+  if (slots <= 0) slots = int((budget - fixed) / kSlotBytes);
+  const int need = chunks_per_tile<MODE>(P.n_lights);
+  if (slots > 2 * need) slots = 2 * need;                               // two whole tiles in flight is plenty
+  if (slots > 64) slots = 64;
+  if (slots < 2) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  P.slots = slots;
+  const size_t smem = size_t(slots) * kSlotBytes + size_t(slots) * 16 + geo + 16;
+  if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  auto kern = tile_kernel<MODE, WANT_POW, TGT>;
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
+  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  long long grid = (long long)d.sms * ctas_per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  P.counter = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
+  kern<<<int(grid), kThreads + 32, smem, st>>>(P);
   return int(cudaGetLastError());
 }
 
 template <int MODE>
 static int launch_l2(const Params& P, bool want_pow, int tgt, cudaStream_t st) {
   if (tgt == SVBRDF_TARGET_F32)
-    return want_pow ? launch<MODE, true, SVBRDF_TARGET_F32>(P, st) : launch<MODE, false, SVBRDF_TARGET_F32>(P, st);
+    return want_pow ? launch_tile<MODE, true, SVBRDF_TARGET_F32>(P, st) : launch_tile<MODE, false, SVBRDF_TARGET_F32>(P, st);
   if (tgt == SVBRDF_TARGET_U8)
-    return want_pow ? launch<MODE, true, SVBRDF_TARGET_U8>(P, st) : launch<MODE, false, SVBRDF_TARGET_U8>(P, st);
+    return want_pow ? launch_tile<MODE, true, SVBRDF_TARGET_U8>(P, st) : launch_tile<MODE, false, SVBRDF_TARGET_U8>(P, st);
   return SVBRDF_E_UNSUPPORTED;
 }
 
@@ -367,8 +750,7 @@ const char* svbrdf_error_string(int code) {
 
 size_t svbrdf_workspace_bytes(int32_t res, int32_t rows) {
   if (res <= 0 || rows <= 0) return 0;
-  const long long texels = (long long)res * rows;
-  return size_t((texels + kThreads - 1) / kThreads) * 4 * sizeof(float);
+  return partial_rows((long long)res * rows) * 4 * sizeof(float) + 16;
 }
 
 int svbrdf_render_fwd(const svbrdf_geom_t* geom, const float* tex, float* out, svbrdf_stream_t stream) {
@@ -377,28 +759,21 @@ int svbrdf_render_fwd(const svbrdf_geom_t* geom, const float* tex, float* out, s
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.out = out;
-  return launch<kModeRender, false, SVBRDF_TARGET_F32>(P, stream);
+  return launch_texel<kModeRender, false, SVBRDF_TARGET_F32>(P, stream);
 }
 
 int svbrdf_render_bwd(const svbrdf_geom_t* geom, const float* tex, const float* grad_out, float* grad_tex, float* grad_pow,
                       void* workspace, svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
-  if (!tex || !grad_out || !grad_tex || (grad_pow && !workspace)) return SVBRDF_E_BADARG;
+  if (!tex || !grad_out || !grad_tex || !workspace) return SVBRDF_E_BADARG;
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = grad_out;
   P.out = grad_tex;
   P.partials = static_cast<float*>(workspace);
   P.scale = float(1.0 / kGamma);
-  int e = grad_pow ? launch<kModeVjp, true, SVBRDF_TARGET_F32>(P, stream) : launch<kModeVjp, false, SVBRDF_TARGET_F32>(P, stream);
-  if (e || !grad_pow) return e;
-  FinalizeParams F{};
-  F.partials = P.partials;
-  F.n_blocks = n_blocks(P);
-  F.grad_scale = P.scale;
-  F.grad_pow = grad_pow;
-  finalize_kernel<<<1, 256, 0, stream>>>(F);
-  return int(cudaGetLastError());
+  P.grad_pow = grad_pow;
+  return grad_pow ? launch_tile<kModeVjp, true, SVBRDF_TARGET_F32>(P, stream) : launch_tile<kModeVjp, false, SVBRDF_TARGET_F32>(P, stream);
 }
 
 int svbrdf_l2_grad(const svbrdf_geom_t* geom, const float* tex, const void* target, int32_t target_dtype, int32_t n_total,
@@ -411,16 +786,10 @@ int svbrdf_l2_grad(const svbrdf_geom_t* geom, const float* tex, const void* targ
   P.out = grad_tex;
   P.partials = static_cast<float*>(workspace);
   P.scale = float(l2_scale(geom, n_total));
-  if (int e = launch_l2<kModeL2Grad>(P, grad_pow != nullptr, target_dtype, stream)) return e;
-  FinalizeParams F{};
-  F.partials = P.partials;
-  F.n_blocks = n_blocks(P);
-  F.loss_norm = 1.0 / (double(n_total) * 3.0 * double(geom->res) * double(geom->res));
-  F.grad_scale = P.scale;
-  F.loss_out = loss_out;
-  F.grad_pow = grad_pow;
-  finalize_kernel<<<1, 256, 0, stream>>>(F);
-  return int(cudaGetLastError());
+  P.loss_norm = 1.0 / (double(n_total) * 3.0 * double(geom->res) * double(geom->res));
+  P.loss_out = loss_out;
+  P.grad_pow = grad_pow;
+  return launch_l2<kModeL2Grad>(P, grad_pow != nullptr, target_dtype, stream);
 }
 
 int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v, const void* target, int32_t target_dtype,
@@ -435,24 +804,12 @@ int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v
   P.io = target;
   P.partials = static_cast<float*>(workspace);
   P.scale = float(l2_scale(geom, geom->n_lights));
-  FinalizeParams F{};
-  F.partials = P.partials;
-  F.n_blocks = n_blocks(P);
-  F.loss_norm = 1.0 / (double(geom->n_lights) * 3.0 * double(geom->res) * double(geom->res));
-  F.grad_scale = P.scale;
-  if (pow_state) {
-    F.pow = const_cast<float*>(geom->light_pow);
-    F.pow_state = pow_state;
-  }
+  P.loss_norm = 1.0 / (double(geom->n_lights) * 3.0 * double(geom->res) * double(geom->res));
+  P.pow_state = pow_state;
   for (int e = 0; e < epochs; ++e) {
     P.adam = make_adam(*adam, adam->step + e);
+    P.loss_out = loss_curve ? loss_curve + e : nullptr;
     if (int err = launch_l2<kModeL2Adam>(P, pow_state != nullptr, target_dtype, stream)) return err;
-    F.adam = P.adam;
-    F.loss_out = loss_curve ? loss_curve + e : nullptr;
-    if (F.loss_out || F.pow) {
-      finalize_kernel<<<1, 256, 0, stream>>>(F);
-      if (cudaError_t err = cudaGetLastError()) return int(err);
-    }
   }
   return 0;
 }

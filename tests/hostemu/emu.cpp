@@ -50,7 +50,7 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
       Texel<T> tx;
       TexelAux<T> ax;
       texel_position(row0 + r, c, res, size, tx.px, tx.py);
-      texel_prologue(t, tx, ax);
+      texel_prologue(t, pw, tx, ax);
       Grads<T> g;
       grads_zero(g);
       for (int i = 0; i < N; ++i) {
@@ -59,17 +59,17 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
         if (mode >= 1)
           for (int ch = 0; ch < 3; ++ch) in3[ch] = io[(size_t(i) * 3 + ch) * plane + p];
         if (mode == 0) {
-          shade_light<T, kRender, COLOC, false>(tx, lg, pw, in3, o3, g);
+          shade_light<T, kRender, COLOC, false>(tx, lg, in3, o3, g);
           for (int ch = 0; ch < 3; ++ch) out[(size_t(i) * 3 + ch) * plane + p] = o3[ch];
         } else if (mode == 1) {
-          shade_light<T, kVjp, COLOC, true>(tx, lg, pw, in3, o3, g);
+          shade_light<T, kVjp, COLOC, true>(tx, lg, in3, o3, g);
         } else {
-          shade_light<T, kL2, COLOC, true>(tx, lg, pw, in3, o3, g);
+          shade_light<T, kL2, COLOC, true>(tx, lg, in3, o3, g);
         }
       }
       if (mode == 0) continue;
       T gt[9];
-      texel_epilogue(tx, ax, g, scale, outer, gt);
+      texel_epilogue<T, COLOC>(tx, ax, pw, g, scale, outer, gt);
       loss_acc += double(g.loss);
       for (int ch = 0; ch < 3; ++ch) gp_acc[ch] += double(g.pw[ch]) * double(scale);
       if (mode == 3) {
@@ -83,7 +83,7 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
     }
   }
   if (loss) *loss = loss_acc / (double(n_total) * 3.0 * double(res) * double(res));
-  if (grad_pow) for (int ch = 0; ch < 3; ++ch) grad_pow[ch] = T(gp_acc[ch]);
+  if (grad_pow) for (int ch = 0; ch < 3; ++ch) grad_pow[ch] = pow_grad(T(gp_acc[ch]), pw[ch]);   // acc = pw_c * dL/dpw_c
 }
 
 template <typename T>

@@ -45,7 +45,8 @@ def test_abi_version_and_errors():
     assert L.svbrdf_error_string(0) == b"success"
     assert b"bad argument" in L.svbrdf_error_string(-1)
     assert b"unsupported" in L.svbrdf_error_string(-2)
-    assert L.svbrdf_workspace_bytes(1024, 1024) == (1024 * 1024 // 256) * 16
+    assert L.svbrdf_workspace_bytes(1024, 1024) == (1024 * 1024 // 256) * 16 + 16      # block partials + finish counter
+    assert L.svbrdf_workspace_bytes(4096, 4096) == (4096 * 4096 // 256) * 16 + 16
     assert L.svbrdf_workspace_bytes(0, 5) == 0
 
 
