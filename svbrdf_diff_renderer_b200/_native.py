@@ -91,9 +91,13 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
-        build_native()
-    L = ctypes.CDLL(LIB_PATH)
+    override = os.environ.get("SVBRDF_B200_LIB")        # development: an alternative build of the same ABI
+    if override:
+        L = ctypes.CDLL(override)
+    else:
+        if needs_build():
+            build_native()
+        L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
     gp, ap = ctypes.POINTER(Geom), ctypes.POINTER(Adam)
     L.svbrdf_abi_version.restype = ctypes.c_int

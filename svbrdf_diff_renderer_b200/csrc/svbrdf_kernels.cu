@@ -28,16 +28,30 @@
 // (everything the reference's capture code emits, capture.py:70-71) take the folded loop body.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "../../include/svbrdf_b200.h"
 #include "svbrdf_core.cuh"
 
 namespace svbrdf {
 
-constexpr int kThreads = 256;          // texels per tile == consumer threads per CTA
+constexpr int kThreads = 256;          // texel_kernel: threads (= texels) per CTA
 constexpr int kPrefetch = 2;           // texel_kernel: lights of io data in flight per thread
+// tile_kernel: consumer warps per CTA (+1 producer warp).  Registers are allocated to a CTA in units of
+// 4 warps, so CW+1 is kept a multiple of 4.  Measured on B200 at 1024^2 x 9 lights (profiles/r01_variants.txt):
+// 15+1 warps, one CTA per SM, 128 registers/thread (no spills) beats 2 x (7+1) warps, and 19+1 / 23+1 warps
+// at 96 / 80 registers: 80.0 vs 89.1 / 84.7 / 89.7 us per step.
+#ifndef SV_CONSUMER_WARPS
+#define SV_CONSUMER_WARPS 15
+#endif
+constexpr int kConsumerWarps = SV_CONSUMER_WARPS;
+constexpr int kTile = 32 * kConsumerWarps;   // texels per tile == consumer threads per CTA
+constexpr int kTileThreads = kTile + 32;     // + the producer warp
 constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
 constexpr int kSlotPlanes = 9;         // planes per ring slot (9 texture channels, or 3 lights x 3)
-constexpr int kConsumerWarps = kThreads / 32;
+#ifndef SV_TILE_MAXNREG
+#define SV_TILE_MAXNREG 128
+#endif
 
 enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3 };
 
@@ -132,10 +146,17 @@ __device__ __forceinline__ void clamp_outer(const float raw[9], float t[9], bool
 // Sums [n][4] partials in double in a fixed order (run-to-run deterministic), writes the loss and
 // the light-power gradient, and — for optim_light — applies Adam to light_pow[3].
 // Every thread of the CTA must call it (it synchronises); threads with tid >= 256 only synchronise.
-__device__ __forceinline__ void finalize_block(const Params& P, int n, double (*s)[4], int tid) {
-  if (tid < 256) {
+__device__ __forceinline__ void finalize_block(const Params& P, int n, double (*s)[4], int tid, int nthreads) {
+  // `nthreads` = CTA size; the first min(nthreads, 256) threads accumulate into s[256][4]
+  const int np = nthreads < 256 ? nthreads : 256;
+  for (int z = tid; z < 256; z += nthreads) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[z][c] = 0.0;
+  }
+  __syncthreads();
+  if (tid < np) {
     double acc[4] = {0, 0, 0, 0};
-    for (int b = tid; b < n; b += 256) {
+    for (int b = tid; b < n; b += np) {
       const float4 q = __ldcg(reinterpret_cast<const float4*>(P.partials) + b);
       acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
     }
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
 // Finalisation for texel_kernel launches (one small CTA).
 __global__ void __launch_bounds__(256) finalize_kernel(const Params P, int n_blocks) {
   __shared__ double s[256][4];
-  finalize_block(P, n_blocks, s, threadIdx.x);
+  finalize_block(P, n_blocks, s, threadIdx.x, 256);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -326,11 +347,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)      // suspend-time hint: park the warp instead of polling
       : "memory");
   return ok != 0;
 }
@@ -346,11 +367,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-constexpr int kSlotBytes = kSlotPlanes * kThreads * 4;     // 9216
+constexpr int kSlotBytes = kSlotPlanes * kTile * 4;
 
 // Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
 template <int MODE>
-__device__ __forceinline__ int chunks_per_tile(int n_lights) {
+__host__ __device__ __forceinline__ int chunks_per_tile(int n_lights) {
   return 1 + (n_lights + kChunkLights - 1) / kChunkLights + (MODE == kModeL2Adam ? 2 : 0);
 }
 
@@ -361,7 +382,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = P.n_lights, S = P.slots;
-  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  const long long n_tiles = (P.texels + kTile - 1) / kTile;
   float pw[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
@@ -372,7 +393,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p = tile * kThreads + tid;
+    const long long p = tile * kTile + tid;
     const bool valid = p < P.texels;
 
     // ---- texel prologue ----
@@ -382,7 +403,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     {
       const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) raw[k] = s[k * kThreads + tid];
+      for (int k = 0; k < 9; ++k) raw[k] = s[k * kTile + tid];
     }
     release(slot);
     advance();
@@ -413,22 +434,35 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     for (int i0 = 0; i0 < N; i0 += kChunkLights) {
       float in[kChunkLights][3];
       mbar_wait(&full[slot], phase);
-      {
-        const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * kSlotBytes);
+      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * kSlotBytes);
+      if (i0 + kChunkLights <= N) {
+        // full chunk: no per-light guards, so the three independent lights can be interleaved
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kThreads + tid]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * kTile + tid]);
         }
-      }
-      release(slot);
-      advance();
+        release(slot);
+        advance();
 #pragma unroll
-      for (int j = 0; j < kChunkLights; ++j) {
-        if (i0 + j < N) {
+        for (int j = 0; j < kChunkLights; ++j) {
           float o3[3];
-          const LightGeom<float> lg = load_geom<COLOC>(s_geo, i0 + j);
-          shade_light<float, LM, COLOC, WANT_POW>(tx, lg, in[j], o3, g);
+          shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kTile + tid]) : 0.f;
+        }
+        release(slot);
+        advance();
+#pragma unroll
+        for (int j = 0; j < kChunkLights - 1; ++j) {       // a partial chunk holds at most kChunkLights-1 lights
+          if (i0 + j < N) {
+            float o3[3];
+            shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+          }
         }
       }
     }
@@ -442,7 +476,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) mk[k] = s[k * kThreads + tid];
+        for (int k = 0; k < 9; ++k) mk[k] = s[k * kTile + tid];
       }
       release(slot);
       advance();
@@ -450,7 +484,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vk[k] = s[k * kThreads + tid];
+        for (int k = 0; k < 9; ++k) vk[k] = s[k * kTile + tid];
       }
       release(slot);
       advance();
@@ -481,22 +515,30 @@ template <int MODE, int TGT>
 __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ring, unsigned long long* full, unsigned long long* empty) {
   typedef typename IoLoad<TGT>::elem elem;
   const int N = P.n_lights, S = P.slots;
-  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  const long long n_tiles = (P.texels + kTile - 1) / kTile;
   unsigned slot = 0, phase = 0;
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p0 = tile * kThreads;
-    const unsigned len = unsigned(min((long long)kThreads, P.texels - p0));      // texels in this tile (multiple of 4)
-    auto fill = [&](const void* base, size_t elem_bytes, int planes) {
+    const long long p0 = tile * kTile;
+    const unsigned len = unsigned(min((long long)kTile, P.texels - p0));      // texels in this tile (multiple of 4)
+    auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
       // `planes` plane segments of `len` elements each, starting at element p0 of consecutive planes of `base`
       mbar_wait(&empty[slot], phase ^ 1);
-      unsigned char* dst = ring + size_t(slot) * kSlotBytes;
-      const unsigned seg = len * unsigned(elem_bytes);
+      unsigned dst = smem_u32(ring) + slot * unsigned(kSlotBytes);
+      const unsigned bar = smem_u32(&full[slot]);
+      const unsigned seg = len * elem_bytes;
       mbar_expect_tx(&full[slot], seg * planes);
-      for (int j = 0; j < planes; ++j)
-        tma_load_1d(dst + size_t(j) * kThreads * elem_bytes, static_cast<const unsigned char*>(base) + (size_t(j) * P.stride + p0) * elem_bytes,
-                    seg, &full[slot]);
+      const unsigned char* src = static_cast<const unsigned char*>(base) + size_t(p0) * elem_bytes;
+      const size_t src_step = size_t(P.stride) * elem_bytes;
+      const unsigned dst_step = unsigned(kTile) * elem_bytes;
+      for (int j = 0; j < planes; ++j) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                     "r"(seg), "r"(bar)
+                     : "memory");
+        dst += dst_step;
+        src += src_step;
+      }
       advance();
     };
     fill(P.tex, 4, 9);
@@ -512,7 +554,7 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
 }
 
 template <int MODE, bool WANT_POW, int TGT>
-__global__ void __maxnreg__(112) tile_kernel(const Params P) {
+__global__ void __maxnreg__(SV_TILE_MAXNREG) tile_kernel(const Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring [slots * 9216] | barriers full[slots], empty[slots] | light geometry 2*N float4 | reduction scratch
   unsigned char* ring = smem;
@@ -520,7 +562,7 @@ __global__ void __maxnreg__(112) tile_kernel(const Params P) {
   unsigned long long* empty = full + P.slots;
   float4* s_geo = reinterpret_cast<float4*>(empty + P.slots);
   __shared__ float s_red[kConsumerWarps][4];
-  __shared__ double s_fin[kThreads][4];
+  __shared__ double s_fin[256][4];
   __shared__ bool s_last;
 
   const int tid = threadIdx.x;
@@ -532,18 +574,18 @@ __global__ void __maxnreg__(112) tile_kernel(const Params P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  const bool coloc = stage_lights(P, s_geo, tid, kThreads + 32);     // includes __syncthreads
+  const bool coloc = stage_lights(P, s_geo, tid, kTileThreads);     // includes __syncthreads
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tid >= kThreads) {
-    if (tid == kThreads) tile_producer<MODE, TGT>(P, ring, full, empty);
+  if (tid >= kTile) {
+    if (tid == kTile) tile_producer<MODE, TGT>(P, ring, full, empty);
   } else {
     if (coloc) tile_consumer<MODE, true, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
     else tile_consumer<MODE, false, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
   }
 
   // ---- CTA partial -> global; the last CTA to finish reduces all partials (fixed order) ----
-  if (tid < kThreads) {
+  if (tid < kTile) {
     warp_reduce4(acc);
     if ((tid & 31) == 0) {
 #pragma unroll
@@ -566,7 +608,7 @@ __global__ void __maxnreg__(112) tile_kernel(const Params P) {
   __syncthreads();
   if (s_last) {
     __threadfence();
-    finalize_block(P, int(gridDim.x), s_fin, tid);
+    finalize_block(P, int(gridDim.x), s_fin, tid, kTileThreads);
     if (tid == 0) *P.counter = 0u;                         // leave the workspace ready for the next launch
   }
 }
@@ -693,9 +735,11 @@ static int env_int(const char* name, int dflt) {
 template <int MODE, bool WANT_POW, int TGT>
 static int launch_tile(Params P, cudaStream_t st) {
   if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  const bool trace = env_int("SVBRDF_B200_TRACE", 0) != 0;
+  if (trace) fprintf(stderr, "[svbrdf] launch_tile mode %d texels %lld N %d\n", MODE, P.texels, P.n_lights);
   Device d;
   if (int e = device_info(&d)) return e;
-  const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 2);
+  const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 1);
   const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
   const size_t fixed = geo + 64 + 2 * 8 * 64;                          // barriers (<= 64 slots) + padding
   const size_t static_smem = 9 * 1024;                                 // s_fin + s_red (static __shared__)
@@ -709,14 +753,20 @@ static int launch_tile(Params P, cudaStream_t st) {
   P.slots = slots;
   const size_t smem = size_t(slots) * kSlotBytes + size_t(slots) * 16 + geo + 16;
   if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (trace) fprintf(stderr, "[svbrdf] slots %d smem %zu sms %d optin %d\n", slots, smem, d.sms, d.smem_optin);
   auto kern = tile_kernel<MODE, WANT_POW, TGT>;
   if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
-  const long long n_tiles = (P.texels + kThreads - 1) / kThreads;
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
+  if (trace) fprintf(stderr, "[svbrdf] attribute set\n");
+  const long long n_tiles = (P.texels + kTile - 1) / kTile;
   long long grid = (long long)d.sms * ctas_per_sm;
   if (grid > n_tiles) grid = n_tiles;
   P.counter = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
-  kern<<<int(grid), kThreads + 32, smem, st>>>(P);
-  return int(cudaGetLastError());
+  if (trace) fprintf(stderr, "[svbrdf] launching grid %lld\n", grid);
+  kern<<<int(grid), kTileThreads, smem, st>>>(P);
+  const int rc = int(cudaGetLastError());
+  if (trace) fprintf(stderr, "[svbrdf] launched rc %d\n", rc);
+  return rc;
 }
 
 template <int MODE>

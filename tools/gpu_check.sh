@@ -9,6 +9,14 @@ mkdir -p $OUT
 export SVBRDF_B200_QUIET=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 echo "== build" ; python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2
+echo "== tma sanity (short timeout: a pipeline deadlock must not eat the budget)"
+timeout 120 python tools/kernel_bench.py --res 256 --steps 3 --mats 2 --variants "tma2;tma2s4" > $OUT/sanity.log 2>&1
+SANITY=$?
+tail -4 $OUT/sanity.log
+if [ $SANITY -ne 0 ]; then
+  echo "!! tile_kernel sanity failed or hung -> forcing the LDG kernel for the rest of this visit"
+  export SVBRDF_B200_FORCE_LDG=1
+fi
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
   echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee $OUT/pytest_gpu_$TAG.txt
