@@ -178,6 +178,16 @@ SV_HD void texel_position(int row, int col, int res, float size, T& px, T& py) {
   py = T(-fy);
 }
 
+// Same with the division replaced by a multiplication with 1/res (what torch's CUDA division by a
+// scalar does as well): identical for power-of-two resolutions, within 1 ulp of the position otherwise.
+template <typename T>
+SV_HD void texel_position_rcp(int row, int col, float inv_res, float size, T& px, T& py) {
+  const float fx = ((float(col) + 0.5f) * inv_res - 0.5f) * size;
+  const float fy = ((float(row) + 0.5f) * inv_res - 0.5f) * size;
+  px = T(fx);
+  py = T(-fy);
+}
+
 // Prologue: 9 channels -> material parameters.  `t` must already be clamped to [-1,1]
 // by the caller when the outer clamp of svbrdf.py:60 applies.
 template <typename T>

@@ -49,6 +49,14 @@ constexpr int kTile = 32 * kConsumerWarps;   // texels per tile == consumer thre
 constexpr int kTileThreads = kTile + 32;     // + the producer warp
 constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
 constexpr int kSlotPlanes = 9;         // planes per ring slot (9 texture channels, or 3 lights x 3)
+// SV_STASH: park the values only the epilogue needs (raw texel, gamma derivatives, normal reconstruction:
+// 29 floats per texel) in shared memory while the light loop runs, instead of in registers: the compiler
+// then stops rematerialising per-texel constants inside the loop.  Measured (profiles/r01_variants.txt):
+// 1403 -> 1285 us at 2048^2 x 64 lights, neutral at 9 lights.
+#ifndef SV_STASH
+#define SV_STASH 1
+#endif
+constexpr int kStashFloats = 29;
 #ifndef SV_TILE_MAXNREG
 #define SV_TILE_MAXNREG 128
 #endif
@@ -68,6 +76,8 @@ struct Params {
   long long stride;      // plane stride in elements
   long long texels;      // rows * res
   float size;
+  float inv_res;          // 1/res
+  unsigned long long res_magic;   // floor(2^64/res)+1: row = umul64hi(p, magic) for p < 2^32
   int res;
   int row_offset;
   int n_lights;
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
   {
     const int row = int(pc / P.res);
     const int col = int(pc - (long long)row * P.res);
-    texel_position(row + P.row_offset, col, P.res, P.size, tx.px, tx.py);
+    texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
   }
   texel_prologue(t, pw, tx, ax);
   Grads<float> g;
@@ -377,7 +387,7 @@ __host__ __device__ __forceinline__ int chunks_per_tile(int n_lights) {
 
 template <int MODE, bool COLOC, bool WANT_POW, int TGT>
 __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
-                                               unsigned long long* full, unsigned long long* empty, float loss_acc[4]) {
+                                               unsigned long long* full, unsigned long long* empty, float* stash, float loss_acc[4]) {
   typedef typename IoLoad<TGT>::elem elem;
   constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -418,15 +428,28 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       const long long pc = valid ? p : 0;
       int row, col;
       if (P.texels < (1ll << 32)) {
-        row = int(unsigned(pc) / unsigned(P.res));
+        row = int(__umul64hi((unsigned long long)pc, P.res_magic));        // exact floor(pc/res) for pc < 2^32
         col = int(unsigned(pc) - unsigned(row) * unsigned(P.res));
       } else {
         row = int(pc / P.res);
         col = int(pc - (long long)row * P.res);
       }
-      texel_position(row + P.row_offset, col, P.res, P.size, tx.px, tx.py);
+      texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
     }
     texel_prologue(t, pw, tx, ax);
+#if SV_STASH
+    {
+      float* st = stash + tid;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st[k * kTile] = raw[k];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) st[(9 + k) * kTile] = ax.dpow[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { st[(16 + k) * kTile] = ax.d[k]; st[(19 + k) * kTile] = ax.oms[k]; }
+      st[22 * kTile] = ax.rough; st[23 * kTile] = ax.alpha;
+      st[24 * kTile] = ax.mx; st[25 * kTile] = ax.my; st[26 * kTile] = ax.mz; st[27 * kTile] = ax.rlen;
+    }
+#endif
     Grads<float> g;
     grads_zero(g);
 
@@ -468,6 +491,23 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     }
 
     // ---- epilogue ----
+#if SV_STASH
+    {
+      const volatile float* st = stash + tid;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = st[k * kTile];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ax.dpow[k] = st[(9 + k) * kTile];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { ax.d[k] = st[(16 + k) * kTile]; ax.oms[k] = st[(19 + k) * kTile]; }
+      ax.rough = st[22 * kTile]; ax.alpha = st[23 * kTile];
+      ax.mx = st[24 * kTile]; ax.my = st[25 * kTile]; ax.mz = st[26 * kTile]; ax.rlen = st[27 * kTile];
+      clamp_outer<MODE>(raw, t, outer);
+      ax.in3 = (t[3] >= -1.f) && (t[3] <= 1.f);
+      ax.in4 = (t[4] >= -1.f) && (t[4] <= 1.f);
+      ax.planar_free = (ax.mx * ax.mx + ax.my * ax.my) <= (1.f - float(kEps));
+    }
+#endif
     float gt[9];
     texel_epilogue<float, COLOC>(tx, ax, pw, g, P.scale, outer, gt);
     if (MODE == kModeL2Adam) {
@@ -489,19 +529,28 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       release(slot);
       advance();
       if (valid) {
+        float* __restrict__ pt = P.tex + p;
+        float* __restrict__ pm = P.m + p;
+        float* __restrict__ pv = P.v + p;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-          const long long idx = k * P.stride + p;
           float pk = raw[k];
           adam_update(pk, mk[k], vk[k], gt[k], P.adam);
-          P.tex[idx] = pk;
-          P.m[idx] = mk[k];
-          P.v[idx] = vk[k];
+          *pt = pk;
+          *pm = mk[k];
+          *pv = vk[k];
+          pt += P.stride;
+          pm += P.stride;
+          pv += P.stride;
         }
       }
     } else if (valid) {
+      float* __restrict__ po = P.out + p;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) P.out[k * P.stride + p] = gt[k];
+      for (int k = 0; k < 9; ++k) {
+        *po = gt[k];
+        po += P.stride;
+      }
     }
     if (valid) {
       loss_acc[0] += g.loss;
@@ -561,6 +610,7 @@ __global__ void __maxnreg__(SV_TILE_MAXNREG) tile_kernel(const Params P) {
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots) * kSlotBytes);
   unsigned long long* empty = full + P.slots;
   float4* s_geo = reinterpret_cast<float4*>(empty + P.slots);
+  float* stash = reinterpret_cast<float*>(s_geo + 2 * P.n_lights);
   __shared__ float s_red[kConsumerWarps][4];
   __shared__ double s_fin[256][4];
   __shared__ bool s_last;
@@ -580,8 +630,8 @@ __global__ void __maxnreg__(SV_TILE_MAXNREG) tile_kernel(const Params P) {
   if (tid >= kTile) {
     if (tid == kTile) tile_producer<MODE, TGT>(P, ring, full, empty);
   } else {
-    if (coloc) tile_consumer<MODE, true, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
-    else tile_consumer<MODE, false, WANT_POW, TGT>(P, s_geo, ring, full, empty, acc);
+    if (coloc) tile_consumer<MODE, true, WANT_POW, TGT>(P, s_geo, ring, full, empty, stash, acc);
+    else tile_consumer<MODE, false, WANT_POW, TGT>(P, s_geo, ring, full, empty, stash, acc);
   }
 
   // ---- CTA partial -> global; the last CTA to finish reduces all partials (fixed order) ----
@@ -672,6 +722,8 @@ static Params base_params(const svbrdf_geom_t* g) {
   P.stride = g->plane_stride ? g->plane_stride : P.texels;
   P.size = g->size;
   P.res = g->res;
+  P.inv_res = 1.0f / float(g->res);
+  P.res_magic = ~0ull / (unsigned long long)g->res + 1ull;
   P.row_offset = g->row_offset;
   P.n_lights = g->n_lights;
   return P;
@@ -741,7 +793,8 @@ static int launch_tile(Params P, cudaStream_t st) {
   if (int e = device_info(&d)) return e;
   const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 1);
   const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
-  const size_t fixed = geo + 64 + 2 * 8 * 64;                          // barriers (<= 64 slots) + padding
+  const size_t stash_bytes = SV_STASH ? size_t(kStashFloats) * kTile * 4 : 0;
+  const size_t fixed = geo + stash_bytes + 64 + 2 * 8 * 64;            // barriers (<= 64 slots) + padding
   const size_t static_smem = 9 * 1024;                                 // s_fin + s_red (static __shared__)
   const size_t budget = size_t(228 * 1024) / ctas_per_sm - 1024 - static_smem;
   int slots = env_int("SVBRDF_B200_SLOTS", 0);
@@ -751,7 +804,7 @@ static int launch_tile(Params P, cudaStream_t st) {
   if (slots > 64) slots = 64;
   if (slots < 2) return launch_texel<MODE, WANT_POW, TGT>(P, st);
   P.slots = slots;
-  const size_t smem = size_t(slots) * kSlotBytes + size_t(slots) * 16 + geo + 16;
+  const size_t smem = size_t(slots) * kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
   if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
   if (trace) fprintf(stderr, "[svbrdf] slots %d smem %zu sms %d optin %d\n", slots, smem, d.sms, d.smem_optin);
   auto kern = tile_kernel<MODE, WANT_POW, TGT>;
