@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--lights", type=int, default=LIGHTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--view-sharded", action="store_true", help="also time the view-sharded (strong-scaling) mode; default on when N>1")
+    ap.add_argument("--vs-res", type=int, default=2048)
+    ap.add_argument("--vs-lights", type=int, default=256)
     return ap.parse_args()
 
 
@@ -295,7 +298,7 @@ def run_b200_arm(args):
         pass
     achieved = algo_bytes / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "svbrdf::texel_kernel<kModeL2Adam> (fused render+L2+backward+Adam)", "kernel_ms": ms_k,
+                "kernel": "svbrdf::tile_kernel<kModeL2Adam> (persistent TMA-pipelined fused render+L2+backward+Adam)", "kernel_ms": ms_k,
                 "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_texel": 216 + 12 * n, "peak_source": peak_src,
                 "samples_per_s_kernel_only": samples_per_step / (ms_k * 1e-3)}
 
@@ -346,6 +349,11 @@ def run_b200_arm(args):
                    "d2h_bytes_per_call": host_out.numel() * 4 + 4 * JOB_EPOCHS,
                    "what": "SvbrdfOptim.optim(20 epochs): pinned-host targets + init maps uploaded, 20 fused epochs, maps + loss curve downloaded"}
 
+    # ---- view-sharded mode: ONE material, lights split over the ranks, NCCL all-reduce of the gradient ----
+    view = None
+    if args.view_sharded or world > 1:
+        view = view_sharded_bench(args, dev, world, rank, barrier)
+
     # ---- cpu baseline (rank 0 only, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -357,12 +365,48 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "clocks": clk.summary(),
-            "gpu_launches": 2 * K, "gpu_launches_what": "per step: texel_kernel<L2Adam> + finalize_kernel (loss reduction)",
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "view_sharded": view, "clocks": clk.summary(),
+            "gpu_launches": K, "gpu_launches_what": "one tile_kernel<L2Adam> launch per step (loss reduction fused: last CTA finalises)",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def view_sharded_bench(args, dev, world, rank, barrier):
+    """Strong scaling of one material: `vs_res`^2 texels x `vs_lights` lights in total, lights sharded over the ranks
+    (SURVEY.md §8(e)); per epoch every rank runs svbrdf_l2_grad on its lights per row band, all-reduces the band
+    gradient over NCCL (overlapped with the next band's kernel) and applies the identical Adam update."""
+    import torch.distributed as dist
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import sharding, synth
+    res, n = args.vs_res, args.vs_lights
+    cl = synth.calibration(n)
+    vs = sharding.ViewShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev, bands=4)
+    gt = synth.random_textures(res, 1).to(dev)
+    with th.no_grad():                                   # this rank's targets only
+        tgt = vs.renderer.eval(gt)
+    vs.load_targets(tgt)
+    del tgt
+    vs.init_from_tex(synth.random_textures(res, 2))
+    vs.optim(2, LR)                                      # warm-up (NCCL channels, kernels)
+    epochs = 5
+    barrier()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = vs.optim(epochs, LR)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = th.tensor([ms], device=dev, dtype=th.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    samples = res * res * n * epochs
+    return {"value": samples / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_epoch": ms / epochs, "res": res, "lights_total": n,
+            "lights_per_gpu": vs.n_local, "bands": len(vs.bands), "allreduce_bytes_per_epoch": 9 * res * res * 4,
+            "collective": "NCCL all_reduce(SUM) of the [9,rows,R] band gradients, async, overlapped with the next band's kernel" if world > 1 else "none (1 GPU)",
+            "loss_first_last": [losses[0], losses[-1]]}
 
 
 def main():

@@ -1,0 +1,182 @@
+"""Multi-GPU partitioning of the per-pixel optimisation path (one process per GPU, torch.distributed).
+
+The reference is single-device (``/root/reference/src/scripts.py:68``); both shardings are new
+(SURVEY.md §8(e)):
+
+* **material-sharded** — independent materials are dealt round-robin to the ranks; every rank runs
+  the single-GPU fused loop on its own materials; there is NO data-path collective (only the final
+  losses are gathered on the host).
+
+* **view-sharded** — one material whose light/view stack is split into contiguous shards.  Textures
+  and Adam state are replicated.  Because ``dL/dtex = sum over lights`` and the MSE mean divides by
+  the GLOBAL count ``N_total*3*R*R``, every rank calls ``svbrdf_l2_grad`` with its own lights and
+  ``n_total``; the partial gradients add.  Per epoch, for each row band:
+  ``svbrdf_l2_grad(band)`` -> ``all_reduce(SUM)`` of the band's ``[9,rows,R]`` gradient (NCCL over
+  NVLink/NVSwitch, asynchronous: it overlaps the next band's compute) -> ``svbrdf_adam_apply(band)``.
+  The 4-float ``[loss, dpow]`` vector is reduced once per epoch.  All ranks apply the identical Adam
+  update, so the replicas stay bit-identical without a broadcast.
+
+The arithmetic engine is injectable so the partitioning logic can be exercised with ``gloo`` on CPU
+by the tests (tests/test_sharding_gloo.py plugs in the oracle there); the product engine is
+``NativeEngine`` — the CUDA kernels behind the C ABI, nothing else.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import torch as th
+import torch.distributed as dist
+
+
+def split_range(n: int, world: int, rank: int):
+    """Contiguous, balanced split of ``range(n)``: the first ``n % world`` ranks get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def round_robin(n: int, world: int, rank: int):
+    """Material indices of ``rank``: 38 materials on 8 GPUs -> 5,5,5,5,5,5,4,4."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    return list(range(rank, n, world))
+
+
+def row_bands(res: int, bands: int):
+    """Split the rows of a ``res x res`` image into ``bands`` contiguous bands (multiples of 8 rows when possible)."""
+    bands = max(1, min(bands, res))
+    edges = [((res * b // bands) // 8) * 8 if res >= 8 * bands else res * b // bands for b in range(bands)] + [res]
+    return [(edges[b], edges[b + 1]) for b in range(bands) if edges[b + 1] > edges[b]]
+
+
+class NativeEngine:
+    """The CUDA kernels behind ``include/svbrdf_b200.h`` for one rank's light shard."""
+
+    def __init__(self, renderer):
+        from . import _native as nv
+        self.nv, self.r = nv, renderer
+        self.L = nv.lib()
+        self._ws = {}
+
+    def _workspace(self, rows):
+        if rows not in self._ws:
+            self._ws[rows] = self.nv.workspace(self.r.res, rows, self.r.device)
+        return self._ws[rows]
+
+    def l2_grad_band(self, tex, targets, n_total, band, grad, loss_out):
+        """One row band, all tensors band-contiguous: tex/grad ``[9,rows,R]``, targets ``[n_local,3,rows,R]``.
+        grad <- this shard's share of dL/dtex for the band; loss_out[0] <- its share of the loss."""
+        nv, r = self.nv, self.r
+        r0, r1 = band
+        geom = r._geom(r._pow, rows=r1 - r0, row_offset=r0)
+        code = self.L.svbrdf_l2_grad(ctypes.byref(geom), nv.ptr(tex), nv.ptr(targets), nv.target_dtype_code(targets), n_total,
+                                     nv.ptr(grad), nv.ptr(loss_out), None, nv.ptr(self._workspace(r1 - r0)), nv.stream_ptr(r.device))
+        nv.check(code, "svbrdf_l2_grad")
+
+    def adam_apply(self, p, m, v, g, step, lr):
+        nv = self.nv
+        a = nv.Adam(float(lr), 0.9, 0.999, 1e-8, int(step))
+        nv.check(self.L.svbrdf_adam_apply(nv.ptr(p), nv.ptr(m), nv.ptr(v), nv.ptr(g), p.numel(), ctypes.byref(a), nv.stream_ptr(p.device)),
+                 "svbrdf_adam_apply")
+
+
+class ViewShardedOptim:
+    """One material, lights split across the ranks of ``group`` (default: the world group).
+
+    ``cl`` is the FULL calibration ``[camera_pos[N,3], light_pos[N,3], light_pow[3]]``; each rank keeps
+    lights ``split_range(N, world, rank)`` and loads only those targets.
+
+    Storage is band-major: textures, Adam state, gradient and targets are kept as one contiguous block per
+    row band, so a band is a self-contained launch (``rows``/``row_offset`` of the ABI) and its gradient is
+    one contiguous NCCL buffer.
+    """
+
+    def __init__(self, res, n_total, size, cl, device, group=None, engine_factory=None, bands=4):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.res, self.n_total, self.size, self.device = res, n_total, float(size), th.device(device)
+        self.start, self.end = split_range(n_total, self.world, self.rank)
+        self.n_local = self.end - self.start
+        if self.n_local < 1:
+            raise RuntimeError(f"rank {self.rank}: no lights to own ({n_total} lights on {self.world} ranks)")
+        self.local_cl = [cl[0][self.start:self.end].contiguous(), cl[1][self.start:self.end].contiguous(), cl[2]]
+        if engine_factory is None:
+            from .microfacet import Microfacet
+            self.renderer = Microfacet(res, self.n_local, size, [c.to(self.device) for c in self.local_cl], self.device)
+            self.engine = NativeEngine(self.renderer)
+        else:
+            self.renderer = None
+            self.engine = engine_factory(self)
+        self.bands = row_bands(res, bands)
+        self.losses = []
+
+    def load_targets(self, local_targets):
+        """``[n_local,3,R,R]`` — this rank's shard of the target stack (float32 or uint8); re-laid out per band once."""
+        if tuple(local_targets.shape) != (self.n_local, 3, self.res, self.res):
+            raise RuntimeError(f"rank {self.rank}: targets must be [{self.n_local},3,{self.res},{self.res}]")
+        self.targets = [local_targets[:, :, r0:r1, :].to(self.device).contiguous() for r0, r1 in self.bands]
+
+    def init_from_tex(self, textures):
+        """Replicated start maps ``[1,9,R,R]``; rank 0's copy wins so replicas start bit-identical."""
+        full = textures.detach().to(device=self.device, dtype=th.float32).contiguous().clone()
+        if self.world > 1:
+            dist.broadcast(full, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        self.tex = [full[0, :, r0:r1, :].contiguous() for r0, r1 in self.bands]
+
+    @property
+    def textures(self):
+        """The current maps as one ``[1,9,R,R]`` tensor (assembled from the bands)."""
+        return th.cat(self.tex, 1).unsqueeze(0)
+
+    def optim(self, epochs, lr):
+        nb = len(self.bands)
+        m = [th.zeros_like(t) for t in self.tex]
+        v = [th.zeros_like(t) for t in self.tex]
+        grad = [th.zeros_like(t) for t in self.tex]
+        scal = th.zeros(nb, dtype=th.float32, device=self.device)
+        curve = th.zeros(max(epochs, 1), dtype=th.float32, device=self.device)
+        for epoch in range(epochs):
+            works = []
+            for b, band in enumerate(self.bands):
+                self.engine.l2_grad_band(self.tex[b], self.targets[b], self.n_total, band, grad[b], scal[b:b + 1])
+                if self.world > 1:       # asynchronous: overlaps the next band's gradient kernel
+                    works.append(dist.all_reduce(grad[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for b in range(nb):
+                if works:
+                    works[b].wait()
+                # identical update on every rank: the replicas stay bit-identical without a broadcast
+                self.engine.adam_apply(self.tex[b], m[b], v[b], grad[b], epoch + 1, lr)
+            curve[epoch] = scal.sum()
+        if self.world > 1 and epochs > 0:
+            dist.all_reduce(curve, op=dist.ReduceOp.SUM, group=self.group)      # loss shares add; once per run
+        self.losses = curve[:epochs].tolist()
+        return self.losses
+
+
+def optimise_materials(n_materials, make_problem, epochs, lr, device, group=None):
+    """Material-sharded driver: ``make_problem(i)`` -> ``(renderer, targets, start_textures)`` for material i.
+
+    Returns ``{material index: (final loss, optimised textures)}`` for this rank's materials and the list of
+    final losses of ALL materials (gathered on the host — the only communication of this mode).
+    """
+    from .svbrdf import SvbrdfOptim
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = {}
+    for i in round_robin(n_materials, world, rank):
+        renderer, targets, tex0 = make_problem(i)
+        opt = SvbrdfOptim(device, renderer)
+        opt.load_targets(targets)
+        opt.init_from_tex(tex0)
+        losses = opt.optim(epochs, lr, None, False, progress=False)
+        mine[i] = (losses[-1] if losses else float("nan"), opt.textures.detach())
+    final = {i: l for i, (l, _) in mine.items()}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, final, group=group)
+        final = {k: val for d in gathered for k, val in d.items()}
+    return mine, [final[i] for i in sorted(final)]
