@@ -50,6 +50,14 @@ struct Fm;
 
 template <>
 struct Fm<float> {
+  typedef bool mask;                       // per-lane predicate type (a pair of bools for the packed type)
+  static constexpr bool kRefine = true;    // MUFU.RSQ needs the Newton step (see rsqrt_dir)
+  static SV_HD mask ge(float a, float b) { return a >= b; }
+  static SV_HD mask le(float a, float b) { return a <= b; }
+  static SV_HD mask eq(float a, float b) { return a == b; }
+  static SV_HD mask mand(mask a, mask b) { return a && b; }
+  static SV_HD mask mtrue() { return true; }
+  static SV_HD float sel(mask m, float a, float b) { return m ? a : b; }
 #if defined(__CUDA_ARCH__)
   static SV_D float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static SV_D float rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -92,6 +100,14 @@ struct Fm<float> {
 
 template <>
 struct Fm<double> {
+  typedef bool mask;
+  static constexpr bool kRefine = false;
+  static SV_HD mask ge(double a, double b) { return a >= b; }
+  static SV_HD mask le(double a, double b) { return a <= b; }
+  static SV_HD mask eq(double a, double b) { return a == b; }
+  static SV_HD mask mand(mask a, mask b) { return a && b; }
+  static SV_HD mask mtrue() { return true; }
+  static SV_HD double sel(mask m, double a, double b) { return m ? a : b; }
   static SV_HD double rcp(double x) { return 1.0 / x; }
   static SV_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static SV_HD double sqrt(double x) { return ::sqrt(x); }
@@ -100,6 +116,64 @@ struct Fm<double> {
   static SV_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static SV_HD double max(double a, double b) { return a > b ? a : b; }
   static SV_HD double min(double a, double b) { return a < b ? a : b; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Packed pair of floats: two texels per thread.  On sm_100 the arithmetic maps to the packed
+// FP32x2 instructions (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of work), which is
+// what an issue-bound elementwise kernel wants; MUFU, min/max and selects stay per component.
+// The host build (tests) implements the same type with scalar operations.
+// ---------------------------------------------------------------------------------------------
+struct V2 {
+  float x, y;
+  SV_HD V2() {}
+  SV_HD V2(float a) : x(a), y(a) {}
+  SV_HD V2(double a) : x(float(a)), y(float(a)) {}
+  SV_HD V2(int a) : x(float(a)), y(float(a)) {}
+  SV_HD V2(float a, float b) : x(a), y(b) {}
+};
+struct M2 {
+  bool x, y;
+};
+#if defined(__CUDA_ARCH__)
+SV_D float2 v2f(const V2& a) { return make_float2(a.x, a.y); }
+SV_D V2 f2v(const float2& a) { return V2(a.x, a.y); }
+SV_D V2 operator+(const V2& a, const V2& b) { return f2v(__fadd2_rn(v2f(a), v2f(b))); }
+SV_D V2 operator-(const V2& a, const V2& b) { return f2v(__fadd2_rn(v2f(a), make_float2(-b.x, -b.y))); }
+SV_D V2 operator*(const V2& a, const V2& b) { return f2v(__fmul2_rn(v2f(a), v2f(b))); }
+SV_D V2 operator-(const V2& a) { return V2(-a.x, -a.y); }
+#else
+SV_HD V2 operator+(const V2& a, const V2& b) { return V2(a.x + b.x, a.y + b.y); }
+SV_HD V2 operator-(const V2& a, const V2& b) { return V2(a.x - b.x, a.y - b.y); }
+SV_HD V2 operator*(const V2& a, const V2& b) { return V2(a.x * b.x, a.y * b.y); }
+SV_HD V2 operator-(const V2& a) { return V2(-a.x, -a.y); }
+#endif
+SV_HD V2& operator+=(V2& a, const V2& b) { a = a + b; return a; }
+SV_HD V2& operator-=(V2& a, const V2& b) { a = a - b; return a; }
+
+template <>
+struct Fm<V2> {
+  typedef M2 mask;
+  typedef Fm<float> S;
+  static constexpr bool kRefine = true;
+  static SV_HD mask ge(const V2& a, const V2& b) { return M2{a.x >= b.x, a.y >= b.y}; }
+  static SV_HD mask le(const V2& a, const V2& b) { return M2{a.x <= b.x, a.y <= b.y}; }
+  static SV_HD mask eq(const V2& a, const V2& b) { return M2{a.x == b.x, a.y == b.y}; }
+  static SV_HD mask mand(mask a, mask b) { return M2{a.x && b.x, a.y && b.y}; }
+  static SV_HD mask mtrue() { return M2{true, true}; }
+  static SV_HD V2 sel(mask m, const V2& a, const V2& b) { return V2(m.x ? a.x : b.x, m.y ? a.y : b.y); }
+  static SV_HD V2 rcp(const V2& a) { return V2(S::rcp(a.x), S::rcp(a.y)); }
+  static SV_HD V2 rsqrt(const V2& a) { return V2(S::rsqrt(a.x), S::rsqrt(a.y)); }
+  static SV_HD V2 sqrt(const V2& a) { return V2(S::sqrt(a.x), S::sqrt(a.y)); }
+  static SV_HD V2 lg2(const V2& a) { return V2(S::lg2(a.x), S::lg2(a.y)); }
+  static SV_HD V2 ex2(const V2& a) { return V2(S::ex2(a.x), S::ex2(a.y)); }
+  static SV_HD V2 max(const V2& a, const V2& b) { return V2(S::max(a.x, b.x), S::max(a.y, b.y)); }
+  static SV_HD V2 min(const V2& a, const V2& b) { return V2(S::min(a.x, b.x), S::min(a.y, b.y)); }
+#if defined(__CUDA_ARCH__)
+  static SV_D V2 fma(const V2& a, const V2& b, const V2& c) { return f2v(__ffma2_rn(v2f(a), v2f(b), v2f(c))); }
+#else
+  static SV_HD V2 fma(const V2& a, const V2& b, const V2& c) { return V2(S::fma(a.x, b.x, c.x), S::fma(a.y, b.y, c.y)); }
+#endif
 };
 
 // rsqrt with one Newton step: y' = y + (y/2)(1 - x y^2).  MUFU.RSQ is good to ~2 ulp; the cosines
@@ -113,7 +187,7 @@ template <typename T>
 SV_HD T rsqrt_dir(T x) {
   T y = Fm<T>::rsqrt(x);
 #if SV_REFINE_RSQRT
-  if (sizeof(T) == 4) {
+  if (Fm<T>::kRefine) {
     const T e = Fm<T>::fma(-x * y, y, T(1));
     y = Fm<T>::fma(T(0.5) * y, e, y);
   }
@@ -154,8 +228,8 @@ struct TexelAux {    // needed again only by the epilogue
   T rough, alpha;
   T mx, my, mz;      // un-normalised normal (clamped nx, ny, reconstructed nz)
   T rlen;            // 1/|m|
-  bool in3, in4;     // inner clamp masks on nx, ny (microfacet.py:65-66)
-  bool planar_free;  // nx^2+ny^2 <= 1-eps: the nz path carries gradient (microfacet.py:67)
+  typename Fm<T>::mask in3, in4;     // inner clamp masks on nx, ny (microfacet.py:65-66)
+  typename Fm<T>::mask planar_free;  // nx^2+ny^2 <= 1-eps: the nz path carries gradient (microfacet.py:67)
 };
 
 template <typename T>
@@ -216,13 +290,13 @@ SV_HD void texel_prologue(const T t[9], const T pw[3], Texel<T>& tx, TexelAux<T>
   tx.k = ax.alpha * T(0.5) + T(kEps);
   tx.omk = T(1) - tx.k;
 
-  ax.in3 = (t[3] >= T(-1)) && (t[3] <= T(1));
-  ax.in4 = (t[4] >= T(-1)) && (t[4] <= T(1));
+  ax.in3 = Fm<T>::mand(Fm<T>::ge(t[3], T(-1)), Fm<T>::le(t[3], T(1)));
+  ax.in4 = Fm<T>::mand(Fm<T>::ge(t[4], T(-1)), Fm<T>::le(t[4], T(1)));
   ax.mx = Fm<T>::min(Fm<T>::max(t[3], T(-1)), T(1));
   ax.my = Fm<T>::min(Fm<T>::max(t[4], T(-1)), T(1));
   const T planar = ax.mx * ax.mx + ax.my * ax.my;
   const T cap = T(1) - T(kEps);
-  ax.planar_free = planar <= cap;
+  ax.planar_free = Fm<T>::le(planar, cap);
   const T pc = Fm<T>::min(planar, cap);
   ax.mz = Fm<T>::sqrt(T(1) - pc);
   ax.rlen = rsqrt_dir(ax.mx * ax.mx + ax.my * ax.my + ax.mz * ax.mz);
@@ -254,30 +328,60 @@ struct LightGeom {   // per light, texture independent
 
 // Radiance -> clamp -> gamma for the 3 channels, and the image gradient gI_c (without its
 // constant factor) in the gradient modes.  fp_c = pw_c * f_c, w = n.l / d^2.
+// SV_MUFU_LITE trades MUFU operations for multiplications where three reciprocals (or the three gamma slopes)
+// can share one MUFU.RCP of a product:  1/a, 1/b, 1/c  from  r = 1/(abc):  1/a = r*(bc), ...
+// 13 -> 9 MUFU per pixel.light on the co-located path at the cost of 12 multiplications — a win when the XU
+// pipe, not the issue slot, is the limiter (the packed FP32x2 kernel).  All factors are bounded away from zero
+// (eps-regularised denominators >= 1e-6, clamped radiance >= 1e-6), so the products stay >= 1e-18.
+#ifndef SV_MUFU_LITE
+#define SV_MUFU_LITE 0
+#endif
+
 template <typename T, int MODE, bool WANT_POW>
 SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out[3], Grads<T>& g, T& gw, T& gQ) {
   typedef Fm<T> F;
   gw = T(0);
   gQ = T(0);
+  T I[3], Icl[3], o[3];
   for (int c = 0; c < 3; ++c) {
-    const T I = fp[c] * w;                                    // microfacet.py:117
-    const T Icl = F::min(F::max(I, T(kEps)), T(1));           // microfacet.py:120
-    const T lg = F::lg2(Icl);
-    if (MODE == kRender) {
-      out[c] = F::ex2(lg * T(1.0 / kGamma));
-      continue;
+    I[c] = fp[c] * w;                                         // microfacet.py:117
+    Icl[c] = F::min(F::max(I[c], T(kEps)), T(1));             // microfacet.py:120
+  }
+  if (MODE == kRender) {
+    for (int c = 0; c < 3; ++c) out[c] = F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma));
+    return;
+  }
+  // d out/d I = (1/gamma) Icl^(1/gamma - 1) = (1/gamma) out/Icl, zero outside the clamp (inclusive edges);
+  // the 1/gamma factor is applied in the epilogue
+  T slope[3];
+#if SV_MUFU_LITE
+  {
+    const T p01 = Icl[0] * Icl[1];
+    const T r = F::rcp(p01 * Icl[2]);
+    const T t2 = r * Icl[2];
+    const T rI[3] = {t2 * Icl[1], t2 * Icl[0], r * p01};
+    for (int c = 0; c < 3; ++c) {
+      o[c] = F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma));
+      slope[c] = o[c] * rI[c];
     }
+  }
+#else
+  for (int c = 0; c < 3; ++c) {
+    const T lg = F::lg2(Icl[c]);
+    if (MODE == kL2) o[c] = F::ex2(lg * T(1.0 / kGamma));
+    slope[c] = F::ex2(lg * T(1.0 / kGamma - 1.0));
+  }
+#endif
+  for (int c = 0; c < 3; ++c) {
     T up;
     if (MODE == kL2) {
-      const T diff = F::ex2(lg * T(1.0 / kGamma)) - io[c];
+      const T diff = o[c] - io[c];
       g.loss = F::fma(diff, diff, g.loss);
       up = diff;
     } else {
       up = io[c];
     }
-    // d out/d I = (1/gamma) Icl^(1/gamma - 1), zero outside the clamp (inclusive edges)
-    const T slope = F::ex2(lg * T(1.0 / kGamma - 1.0));
-    const T gI = (I == Icl) ? up * slope : T(0);
+    const T gI = F::sel(F::eq(I[c], Icl[c]), up * slope[c], T(0));
     const T gfp = gI * w;                                     // dL/d fp_c
     g.kdp[c] += gfp;
     gw = F::fma(gI, fp[c], gw);
@@ -307,7 +411,15 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
   const T Dd = F::fma(T(kPi) * den, den, T(kEps));
   const T gv = F::fma(c, tx.omk, tx.k);
   const T q = F::fma(c2, T(4), T(kEps));
+#if SV_MUFU_LITE
+  const T gq = gv * q;
+  const T rP = F::rcp(Dd * gq);
+  const T rDd = rP * gq;
+  const T tP = rP * Dd;
+  const T rgv = tP * q, rq = tP * gv;
+#else
   const T rDd = F::rcp(Dd), rgv = F::rcp(gv), rq = F::rcp(q);
+#endif
   const T Rc = c * rDd * (rgv * rgv) * rq;                    // Q / (a2 c)
   const T R0 = Rc * c;                                        // Q / a2
   const T Q = tx.a2 * R0;
@@ -396,9 +508,9 @@ SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const
   const T gndl = F::fma(gB * tx.k, rgl2, F::fma(gq * T(4), ndv, gw * inv_d2));
   g.k -= F::fma(gA * ndv * (T(1) - ndv), rgv2, gB * ndl * (T(1) - ndl) * rgl2);
   // clamp(min=0) masks are inclusive; n.h = (n.l + n.v) * rh
-  const T mv = (ndv_raw >= T(0)) ? gndv : T(0);
-  const T ml = (ndl_raw >= T(0)) ? gndl : T(0);
-  const T mh = (ndh_raw >= T(0)) ? gndh * rh : T(0);
+  const T mv = F::sel(F::ge(ndv_raw, T(0)), gndv, T(0));
+  const T ml = F::sel(F::ge(ndl_raw, T(0)), gndl, T(0));
+  const T mh = F::sel(F::ge(ndh_raw, T(0)), gndh * rh, T(0));
   const T cV = (mv + mh) * rv;
   const T cL = (ml + mh) * rl;
   g.n[0] = F::fma(cV, Vx, F::fma(cL, Lx, g.n[0]));
@@ -419,8 +531,8 @@ SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3]
 // when the clamp belongs to the caller's graph (mode B).
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool COLOC>
-SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[3], const Grads<T>& g, T scale, const bool outer[9],
-                          T gt[9]) {
+SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[3], const Grads<T>& g, T scale,
+                          const typename Fm<T>::mask outer[9], T gt[9]) {
   typedef Fm<T> F;
   const T inv_pi = T(1.0 / kPi);
   const T sf = COLOC ? T(1.0 - kSphgColoc) : T(1);
@@ -440,15 +552,15 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[
   const T gmy = (g.n[1] - tx.n[1] * ndg) * ax.rlen;
   const T gmz = (g.n[2] - tx.n[2] * ndg) * ax.rlen;
   // mz = sqrt(1 - clamp(mx^2+my^2, 0, 1-eps))
-  const T gplanar = ax.planar_free ? -gmz * T(0.5) * F::rcp(ax.mz) : T(0);
-  gt[3] = ax.in3 ? F::fma(gplanar, ax.mx + ax.mx, gmx) : T(0);
-  gt[4] = ax.in4 ? F::fma(gplanar, ax.my + ax.my, gmy) : T(0);
-  for (int kk = 0; kk < 9; ++kk) gt[kk] = outer[kk] ? gt[kk] * scale : T(0);
+  const T gplanar = F::sel(ax.planar_free, -gmz * T(0.5) * F::rcp(ax.mz), T(0));
+  gt[3] = F::sel(ax.in3, F::fma(gplanar, ax.mx + ax.mx, gmx), T(0));
+  gt[4] = F::sel(ax.in4, F::fma(gplanar, ax.my + ax.my, gmy), T(0));
+  for (int kk = 0; kk < 9; ++kk) gt[kk] = F::sel(outer[kk], gt[kk] * scale, T(0));
 }
 
 // dL/d light_pow_c from the accumulated sum of gfp_c * fp_c (= pw_c * dL/dpw_c).
 template <typename T>
-SV_HD T pow_grad(T acc, T pw) { return pw != T(0) ? acc / pw : T(0); }
+SV_HD T pow_grad(T acc, T pw) { return pw != T(0) ? acc / pw : T(0); }   // scalar only (finalisation)
 
 // ---------------------------------------------------------------------------------------------
 // Adam (torch/optim/adam.py:531-547, single-tensor path, amsgrad off, weight decay 0).

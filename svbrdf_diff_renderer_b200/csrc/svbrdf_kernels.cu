@@ -37,18 +37,44 @@ namespace svbrdf {
 
 constexpr int kThreads = 256;          // texel_kernel: threads (= texels) per CTA
 constexpr int kPrefetch = 2;           // texel_kernel: lights of io data in flight per thread
-// tile_kernel: consumer warps per CTA (+1 producer warp).  Registers are allocated to a CTA in units of
-// 4 warps, so CW+1 is kept a multiple of 4.  Measured on B200 at 1024^2 x 9 lights (profiles/r01_variants.txt):
-// 15+1 warps, one CTA per SM, 128 registers/thread (no spills) beats 2 x (7+1) warps, and 19+1 / 23+1 warps
-// at 96 / 80 registers: 80.0 vs 89.1 / 84.7 / 89.7 us per step.
+// tile_kernel shapes: CW consumer warps (+1 producer warp) per CTA, LANES texels per consumer thread.
+// Registers are allocated to a CTA in units of 4 warps, so CW+1 is kept a multiple of 4.
+//  * scalar (LANES = 1): 15+1 warps, one CTA per SM, 128 registers/thread, no spills.  Measured on B200 at
+//    1024^2 x 9 lights (profiles/r01_variants.txt): beats 2 x (7+1) warps and 19+1 / 23+1 warps at 96 / 80
+//    registers: 80.0 vs 89.1 / 84.7 / 89.7 us per step.
+//  * packed (LANES = 2): two texels per thread in FP32x2 registers (FFMA2/FMUL2/FADD2), 7+1 warps at up to
+//    255 registers.
+template <int CW, int LANES, int MAXNREG>
+struct TileShape {
+  static constexpr int kCW = CW;
+  static constexpr int kLanes = LANES;
+  static constexpr int kTile = 32 * CW * LANES;      // texels per tile
+  static constexpr int kConsumers = 32 * CW;         // consumer threads
+  static constexpr int kThreads = 32 * (CW + 1);     // + the producer warp
+  static constexpr int kSlotBytes = 9 * kTile * 4;   // one ring slot: 9 plane segments
+  static constexpr int kMaxReg = MAXNREG;
+};
 #ifndef SV_CONSUMER_WARPS
 #define SV_CONSUMER_WARPS 15
 #endif
-constexpr int kConsumerWarps = SV_CONSUMER_WARPS;
-constexpr int kTile = 32 * kConsumerWarps;   // texels per tile == consumer threads per CTA
-constexpr int kTileThreads = kTile + 32;     // + the producer warp
+#ifndef SV_TILE_MAXNREG
+#define SV_TILE_MAXNREG 128
+#endif
+#ifndef SV_PACKED_WARPS
+#define SV_PACKED_WARPS 7
+#endif
+#ifndef SV_PACKED_MAXNREG
+#define SV_PACKED_MAXNREG 255
+#endif
+#ifndef SV_ENABLE_PACKED
+#define SV_ENABLE_PACKED 1
+#endif
+#ifndef SV_PACKED_DEFAULT
+#define SV_PACKED_DEFAULT 0
+#endif
+typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG> ScalarShape;
+typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG> PackedShape;
 constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
-constexpr int kSlotPlanes = 9;         // planes per ring slot (9 texture channels, or 3 lights x 3)
 // SV_STASH: park the values only the epilogue needs (raw texel, gamma derivatives, normal reconstruction:
 // 29 floats per texel) in shared memory while the light loop runs, instead of in registers: the compiler
 // then stops rematerialising per-texel constants inside the loop.  Measured (profiles/r01_variants.txt):
@@ -57,8 +83,10 @@ constexpr int kSlotPlanes = 9;         // planes per ring slot (9 texture channe
 #define SV_STASH 1
 #endif
 constexpr int kStashFloats = 29;
-#ifndef SV_TILE_MAXNREG
-#define SV_TILE_MAXNREG 128
+// Development switch: SV_STREAM_ONLY=1 builds a kernel that moves exactly the same bytes through the same TMA ring
+// and stores but skips the shading math — the streaming ceiling of the pipeline design (profiles/r01_variants.txt).
+#ifndef SV_STREAM_ONLY
+#define SV_STREAM_ONLY 0
 #endif
 
 enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3 };
@@ -88,9 +116,16 @@ struct Params {
   float* loss_out;       // nullable
   float* grad_pow;       // nullable [3]
   float* pow_state;      // nullable: Adam m[3], v[3] of light_pow (optim_light)
-  unsigned int* counter; // finish counter (zero before and after every launch)
+  unsigned int* counters; // [kMaxEpochs] finish tickets (zero before and after every launch)
   int slots;             // ring depth
+  // tile_kernel: `epochs` Adam iterations in ONE launch (texels never interact, so a CTA streams its own tiles
+  // again for the next epoch without any grid-wide synchronisation); per-epoch bias-correction scalars:
+  int epochs;
+  float step_size[64];
+  float inv_sqrt_bc2[64];
 };
+constexpr int kMaxEpochs = 64;          // per launch
+constexpr int kRowsPerEpoch = 4096;     // workspace rows ([loss, gpow x3]) per epoch: one per consumer warp
 
 template <int TGT>
 struct IoLoad;
@@ -198,6 +233,84 @@ __device__ __forceinline__ void finalize_block(const Params& P, int n, double (*
       P.pow_state[3 + tid] = v;
     }
   }
+}
+
+// tile_kernel, end of an epoch: the consumer warps of a CTA combine their [loss, gpow x3] sums through shared memory
+// (consumer-only named barrier — the producer warp is already prefetching the next epoch), the CTA publishes one row
+// and takes a ticket; the CTA that draws the last ticket of epoch `e` sums all rows in a fixed order in double
+// (deterministic), writes the epoch's loss / light-power gradient and (optim_light) applies Adam to light_pow.
+template <int CW>
+__device__ __forceinline__ void epoch_end(const Params& P, int e, float acc[4], float (*s_red)[CW][4], int warp, int lane) {
+  float r[4] = {acc[0], acc[1], acc[2], acc[3]};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+  }
+  float(*buf)[4] = s_red[e & 1];                           // double-buffered: no second barrier needed
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) buf[warp][c] = r[c];
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(CW * 32) : "memory");
+  if (warp != 0) return;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int w = 0; w < CW; ++w) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[c] += buf[w][c];
+  }
+  const int rows = int(gridDim.x);
+  float* base = P.partials + size_t(e) * kRowsPerEpoch * 4;
+  unsigned ticket = 0;
+  if (lane == 0) {
+    __stcg(reinterpret_cast<float4*>(base) + blockIdx.x, make_float4(a[0], a[1], a[2], a[3]));
+    __threadfence();
+    ticket = atomicAdd(P.counters + e, 1u);
+  }
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != unsigned(rows - 1)) return;
+  __threadfence();
+  double t[4] = {0, 0, 0, 0};
+  for (int b = lane; b < rows; b += 32) {
+    const float4 q = __ldcg(reinterpret_cast<const float4*>(base) + b);
+    t[0] += q.x; t[1] += q.y; t[2] += q.z; t[3] += q.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], o);
+  }
+  if (lane == 0) {
+    if (P.loss_out) P.loss_out[e] = float(t[0] * P.loss_norm);
+    P.counters[e] = 0u;                                    // leave the workspace ready for the next launch
+  }
+  if (lane < 3 && (P.grad_pow || P.pow_state)) {
+    const float pw = P.pow[lane];
+    const double tl = lane == 0 ? t[1] : (lane == 1 ? t[2] : t[3]);
+    const float gp = pow_grad(float(tl * double(P.scale)), pw);
+    if (P.grad_pow) P.grad_pow[lane] = gp;
+    if (P.pow_state) {                                      // adam.py:531-547 on 3 elements, IEEE sqrt/div
+      float p = pw, m = P.pow_state[lane], v = P.pow_state[3 + lane];
+      m = m + (gp - m) * P.adam.one_minus_b1;
+      v = v * P.adam.b2 + P.adam.one_minus_b2 * gp * gp;
+      const float denom = sqrtf(v) * P.inv_sqrt_bc2[e] + P.adam.eps;
+      p = p - P.step_size[e] * m / denom;
+      P.pow[lane] = p;
+      P.pow_state[lane] = m;
+      P.pow_state[3 + lane] = v;
+    }
+  }
+}
+
+// Multi-epoch launches: a tile stored in epoch e is re-read by this CTA's TMA loads in epoch e+1.  The stores are
+// made visible to the async proxy and the warp's progress is published one tile LATE — right before the next tile's
+// stores — so the membar finds the previous tile's stores long complete and does not stall the warp.
+__device__ __forceinline__ void publish_tiles(volatile unsigned* s_done, int warp, int lane, unsigned count) {
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) s_done[warp] = count;
 }
 
 __device__ __forceinline__ void warp_reduce4(float r[4]) {
@@ -377,7 +490,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
-constexpr int kSlotBytes = kSlotPlanes * kTile * 4;
 
 // Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
 template <int MODE>
@@ -385,14 +497,14 @@ __host__ __device__ __forceinline__ int chunks_per_tile(int n_lights) {
   return 1 + (n_lights + kChunkLights - 1) / kChunkLights + (MODE == kModeL2Adam ? 2 : 0);
 }
 
-template <int MODE, bool COLOC, bool WANT_POW, int TGT>
+template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
 __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
-                                               unsigned long long* full, unsigned long long* empty, float* stash, float loss_acc[4]) {
+                                               unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4]) {
   typedef typename IoLoad<TGT>::elem elem;
   constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = P.n_lights, S = P.slots;
-  const long long n_tiles = (P.texels + kTile - 1) / kTile;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   float pw[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
@@ -402,8 +514,17 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   auto advance = [&]() { ++it; if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
   auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
 
+  // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
+  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
+  unsigned tiles_finished = 0;
+  for (int e = 0; e < P.epochs; ++e) {
+  AdamStep<float> adam_e = P.adam;
+  adam_e.step_size = P.step_size[e];
+  adam_e.inv_sqrt_bc2 = P.inv_sqrt_bc2[e];
+  float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p = tile * kTile + tid;
+    const long long p = tile * SH::kTile + tid;
     const bool valid = p < P.texels;
 
     // ---- texel prologue ----
@@ -411,9 +532,9 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     bool outer[9];
     mbar_wait(&full[slot], phase);
     {
-      const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+      const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) raw[k] = s[k * kTile + tid];
+      for (int k = 0; k < 9; ++k) raw[k] = s[k * SH::kTile + tid];
     }
     release(slot);
     advance();
@@ -436,18 +557,22 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       }
       texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
     }
+#if SV_STREAM_ONLY
+    tx.px = t[0]; ax.mx = t[1];
+#else
     texel_prologue(t, pw, tx, ax);
-#if SV_STASH
+#endif
+#if SV_STASH && !SV_STREAM_ONLY
     {
       float* st = stash + tid;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) st[k * kTile] = raw[k];
+      for (int k = 0; k < 9; ++k) st[k * SH::kTile] = raw[k];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) st[(9 + k) * kTile] = ax.dpow[k];
+      for (int k = 0; k < 7; ++k) st[(9 + k) * SH::kTile] = ax.dpow[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { st[(16 + k) * kTile] = ax.d[k]; st[(19 + k) * kTile] = ax.oms[k]; }
-      st[22 * kTile] = ax.rough; st[23 * kTile] = ax.alpha;
-      st[24 * kTile] = ax.mx; st[25 * kTile] = ax.my; st[26 * kTile] = ax.mz; st[27 * kTile] = ax.rlen;
+      for (int k = 0; k < 3; ++k) { st[(16 + k) * SH::kTile] = ax.d[k]; st[(19 + k) * SH::kTile] = ax.oms[k]; }
+      st[22 * SH::kTile] = ax.rough; st[23 * SH::kTile] = ax.alpha;
+      st[24 * SH::kTile] = ax.mx; st[25 * SH::kTile] = ax.my; st[26 * SH::kTile] = ax.mz; st[27 * SH::kTile] = ax.rlen;
     }
 #endif
     Grads<float> g;
@@ -457,26 +582,31 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     for (int i0 = 0; i0 < N; i0 += kChunkLights) {
       float in[kChunkLights][3];
       mbar_wait(&full[slot], phase);
-      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * kSlotBytes);
+      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
       if (i0 + kChunkLights <= N) {
         // full chunk: no per-light guards, so the three independent lights can be interleaved
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * kTile + tid]);
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]);
         }
         release(slot);
         advance();
+#if SV_STREAM_ONLY
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
+#else
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
           float o3[3];
           shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
         }
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kTile + tid]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
         }
         release(slot);
         advance();
@@ -491,17 +621,17 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     }
 
     // ---- epilogue ----
-#if SV_STASH
+#if SV_STASH && !SV_STREAM_ONLY
     {
       const volatile float* st = stash + tid;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) raw[k] = st[k * kTile];
+      for (int k = 0; k < 9; ++k) raw[k] = st[k * SH::kTile];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) ax.dpow[k] = st[(9 + k) * kTile];
+      for (int k = 0; k < 7; ++k) ax.dpow[k] = st[(9 + k) * SH::kTile];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { ax.d[k] = st[(16 + k) * kTile]; ax.oms[k] = st[(19 + k) * kTile]; }
-      ax.rough = st[22 * kTile]; ax.alpha = st[23 * kTile];
-      ax.mx = st[24 * kTile]; ax.my = st[25 * kTile]; ax.mz = st[26 * kTile]; ax.rlen = st[27 * kTile];
+      for (int k = 0; k < 3; ++k) { ax.d[k] = st[(16 + k) * SH::kTile]; ax.oms[k] = st[(19 + k) * SH::kTile]; }
+      ax.rough = st[22 * SH::kTile]; ax.alpha = st[23 * SH::kTile];
+      ax.mx = st[24 * SH::kTile]; ax.my = st[25 * SH::kTile]; ax.mz = st[26 * SH::kTile]; ax.rlen = st[27 * SH::kTile];
       clamp_outer<MODE>(raw, t, outer);
       ax.in3 = (t[3] >= -1.f) && (t[3] <= 1.f);
       ax.in4 = (t[4] >= -1.f) && (t[4] <= 1.f);
@@ -509,25 +639,31 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     }
 #endif
     float gt[9];
+#if SV_STREAM_ONLY
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gt[k] = g.loss + tx.px;
+#else
     texel_epilogue<float, COLOC>(tx, ax, pw, g, P.scale, outer, gt);
+#endif
     if (MODE == kModeL2Adam) {
       float mk[9], vk[9];
       mbar_wait(&full[slot], phase);
       {
-        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) mk[k] = s[k * kTile + tid];
+        for (int k = 0; k < 9; ++k) mk[k] = s[k * SH::kTile + tid];
       }
       release(slot);
       advance();
       mbar_wait(&full[slot], phase);
       {
-        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * kSlotBytes);
+        const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vk[k] = s[k * kTile + tid];
+        for (int k = 0; k < 9; ++k) vk[k] = s[k * SH::kTile + tid];
       }
       release(slot);
       advance();
+      if (P.epochs > 1 && tiles_finished > 0 && tiles_finished % publish_every == 0) publish_tiles(s_done, tid >> 5, lane, tiles_finished);
       if (valid) {
         float* __restrict__ pt = P.tex + p;
         float* __restrict__ pm = P.m + p;
@@ -535,7 +671,11 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
           float pk = raw[k];
-          adam_update(pk, mk[k], vk[k], gt[k], P.adam);
+#if SV_STREAM_ONLY
+          pk += gt[k]; mk[k] += 1.f; vk[k] += 1.f;
+#else
+          adam_update(pk, mk[k], vk[k], gt[k], adam_e);
+#endif
           *pt = pk;
           *pm = mk[k];
           *pv = vk[k];
@@ -557,30 +697,285 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
       for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c];
     }
+    ++tiles_finished;
+  }
+  epoch_end<SH::kCW>(P, e, loss_acc, s_red, tid >> 5, lane);
   }
 }
 
-template <int MODE, int TGT>
-__device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ring, unsigned long long* full, unsigned long long* empty) {
+// Two texels per thread, packed FP32x2 arithmetic (core instantiated with T = V2).  Thread `tid` owns texels
+// 2*tid and 2*tid+1 of the tile: LDS.64 from the ring, STG.64 to global.
+template <int TGT>
+struct IoLoad2;
+template <>
+struct IoLoad2<SVBRDF_TARGET_F32> {
+  static __device__ __forceinline__ V2 at(const unsigned char* slot, int plane, int tile, int tid) {
+    const float2 q = reinterpret_cast<const float2*>(slot + size_t(plane) * tile * 4)[tid];
+    return V2(q.x, q.y);
+  }
+};
+template <>
+struct IoLoad2<SVBRDF_TARGET_U8> {
+  static __device__ __forceinline__ V2 at(const unsigned char* slot, int plane, int tile, int tid) {
+    const uchar2 q = reinterpret_cast<const uchar2*>(slot + size_t(plane) * tile)[tid];
+    return V2(IoLoad<SVBRDF_TARGET_U8>::decode(q.x), IoLoad<SVBRDF_TARGET_U8>::decode(q.y));
+  }
+};
+
+template <bool COLOC>
+__device__ __forceinline__ LightGeom<V2> load_geom2(const float4* __restrict__ s_geo, int i) {
+  LightGeom<V2> lg;
+  const float4 a = s_geo[2 * i];
+  lg.cx = V2(a.x); lg.cy = V2(a.y); lg.cz = V2(a.z); lg.cz2 = V2(a.w);
+  if (!COLOC) {
+    const float4 b = s_geo[2 * i + 1];
+    lg.lx = V2(b.x); lg.ly = V2(b.y); lg.lz = V2(b.z); lg.lz2 = V2(b.w);
+  }
+  return lg;
+}
+
+template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
+__device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
+                                                unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4]) {
+  typedef V2 T;
+  typedef Fm<V2> F;
+  constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
+  constexpr bool kClamp = (MODE == kModeL2Grad || MODE == kModeL2Adam);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = P.n_lights, S = P.slots;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
+  const T pw[3] = {T(P.pow[0]), T(P.pow[1]), T(P.pow[2])};
+  const T scale(P.scale);
+
+  unsigned slot = 0, phase = 0;
+  auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
+  auto clamp9 = [&](const T raw[9], T t[9], M2 outer[9]) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (kClamp) {   // the clamp of svbrdf.py:60
+        outer[k] = F::mand(F::ge(raw[k], T(-1.f)), F::le(raw[k], T(1.f)));
+        t[k] = F::min(F::max(raw[k], T(-1.f)), T(1.f));
+      } else {
+        outer[k] = F::mtrue();
+        t[k] = raw[k];
+      }
+    }
+  };
+
+  // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
+  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
+  unsigned tiles_finished = 0;
+  for (int e = 0; e < P.epochs; ++e) {
+  AdamStep<float> adam_e = P.adam;
+  adam_e.step_size = P.step_size[e];
+  adam_e.inv_sqrt_bc2 = P.inv_sqrt_bc2[e];
+  float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p = tile * SH::kTile + 2 * tid;          // first of this thread's two texels
+    const bool valid = p < P.texels;                          // texels % 4 == 0: both or neither
+
+    // ---- texel prologue ----
+    T raw[9], t[9];
+    M2 outer[9];
+    mbar_wait(&full[slot], phase);
+    {
+      const unsigned char* s = ring + size_t(slot) * SH::kSlotBytes;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = IoLoad2<SVBRDF_TARGET_F32>::at(s, k, SH::kTile, tid);
+    }
+    release(slot);
+    advance();
+    if (!valid) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = T(0.f);
+    }
+    clamp9(raw, t, outer);
+    Texel<T> tx;
+    TexelAux<T> ax;
+    {
+      const long long pc = valid ? p : 0;
+      float px[2], py[2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const long long q = pc + l;
+        int row, col;
+        if (P.texels < (1ll << 32)) {
+          row = int(__umul64hi((unsigned long long)q, P.res_magic));
+          col = int(unsigned(q) - unsigned(row) * unsigned(P.res));
+        } else {
+          row = int(q / P.res);
+          col = int(q - (long long)row * P.res);
+        }
+        texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, px[l], py[l]);
+      }
+      tx.px = T(px[0], px[1]);
+      tx.py = T(py[0], py[1]);
+    }
+    texel_prologue(t, pw, tx, ax);
+#if SV_STASH
+    {
+      float2* st = reinterpret_cast<float2*>(stash) + tid;
+      auto put = [&](int k, const T& x) { st[k * SH::kConsumers] = make_float2(x.x, x.y); };
+#pragma unroll
+      for (int k = 0; k < 9; ++k) put(k, raw[k]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) put(9 + k, ax.dpow[k]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { put(16 + k, ax.d[k]); put(19 + k, ax.oms[k]); }
+      put(22, ax.rough); put(23, ax.alpha); put(24, ax.mx); put(25, ax.my); put(26, ax.mz); put(27, ax.rlen);
+    }
+#endif
+    Grads<T> g;
+    grads_zero(g);
+
+    // ---- lights, 3 per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+      T in[kChunkLights][3];
+      mbar_wait(&full[slot], phase);
+      const unsigned char* s = ring + size_t(slot) * SH::kSlotBytes;
+      if (i0 + kChunkLights <= N) {
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad2<TGT>::at(s, j * 3 + c, SH::kTile, tid);
+        }
+        release(slot);
+        advance();
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+          T o3[3];
+          shade_light<T, LM, COLOC, WANT_POW>(tx, load_geom2<COLOC>(s_geo, i0 + j), in[j], o3, g);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad2<TGT>::at(s, j * 3 + c, SH::kTile, tid) : T(0.f);
+        }
+        release(slot);
+        advance();
+#pragma unroll
+        for (int j = 0; j < kChunkLights - 1; ++j) {
+          if (i0 + j < N) {
+            T o3[3];
+            shade_light<T, LM, COLOC, WANT_POW>(tx, load_geom2<COLOC>(s_geo, i0 + j), in[j], o3, g);
+          }
+        }
+      }
+    }
+
+    // ---- epilogue ----
+#if SV_STASH
+    {
+      const volatile float2* st = reinterpret_cast<const volatile float2*>(stash) + tid;
+      auto get = [&](int k) { const float2 q = make_float2(st[k * SH::kConsumers].x, st[k * SH::kConsumers].y); return T(q.x, q.y); };
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = get(k);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ax.dpow[k] = get(9 + k);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { ax.d[k] = get(16 + k); ax.oms[k] = get(19 + k); }
+      ax.rough = get(22); ax.alpha = get(23); ax.mx = get(24); ax.my = get(25); ax.mz = get(26); ax.rlen = get(27);
+      clamp9(raw, t, outer);
+      ax.in3 = F::mand(F::ge(t[3], T(-1.f)), F::le(t[3], T(1.f)));
+      ax.in4 = F::mand(F::ge(t[4], T(-1.f)), F::le(t[4], T(1.f)));
+      ax.planar_free = F::le(ax.mx * ax.mx + ax.my * ax.my, T(1.f - float(kEps)));
+    }
+#endif
+    T gt[9];
+    texel_epilogue<T, COLOC>(tx, ax, pw, g, scale, outer, gt);
+    if (MODE == kModeL2Adam) {
+      T mk[9], vk[9];
+      mbar_wait(&full[slot], phase);
+      {
+        const unsigned char* s = ring + size_t(slot) * SH::kSlotBytes;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mk[k] = IoLoad2<SVBRDF_TARGET_F32>::at(s, k, SH::kTile, tid);
+      }
+      release(slot);
+      advance();
+      mbar_wait(&full[slot], phase);
+      {
+        const unsigned char* s = ring + size_t(slot) * SH::kSlotBytes;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vk[k] = IoLoad2<SVBRDF_TARGET_F32>::at(s, k, SH::kTile, tid);
+      }
+      release(slot);
+      advance();
+      if (P.epochs > 1 && tiles_finished > 0 && tiles_finished % publish_every == 0) publish_tiles(s_done, tid >> 5, lane, tiles_finished);
+      if (valid) {
+        AdamStep<T> a;
+        a.one_minus_b1 = T(adam_e.one_minus_b1); a.b2 = T(adam_e.b2); a.one_minus_b2 = T(adam_e.one_minus_b2);
+        a.step_size = T(adam_e.step_size); a.inv_sqrt_bc2 = T(adam_e.inv_sqrt_bc2); a.eps = T(adam_e.eps);
+        float* __restrict__ pt = P.tex + p;
+        float* __restrict__ pm = P.m + p;
+        float* __restrict__ pv = P.v + p;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          T pk = raw[k];
+          adam_update(pk, mk[k], vk[k], gt[k], a);
+          *reinterpret_cast<float2*>(pt) = make_float2(pk.x, pk.y);
+          *reinterpret_cast<float2*>(pm) = make_float2(mk[k].x, mk[k].y);
+          *reinterpret_cast<float2*>(pv) = make_float2(vk[k].x, vk[k].y);
+          pt += P.stride;
+          pm += P.stride;
+          pv += P.stride;
+        }
+      }
+    } else if (valid) {
+      float* __restrict__ po = P.out + p;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        *reinterpret_cast<float2*>(po) = make_float2(gt[k].x, gt[k].y);
+        po += P.stride;
+      }
+    }
+    if (valid) {
+      loss_acc[0] += g.loss.x + g.loss.y;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c].x + g.pw[c].y;
+    }
+    ++tiles_finished;
+  }
+  epoch_end<SH::kCW>(P, e, loss_acc, s_red, tid >> 5, lane);
+  }
+}
+
+template <int MODE, int TGT, typename SH>
+__device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ring, unsigned long long* full, unsigned long long* empty,
+                                              volatile unsigned* s_done) {
   typedef typename IoLoad<TGT>::elem elem;
   const int N = P.n_lights, S = P.slots;
-  const long long n_tiles = (P.texels + kTile - 1) / kTile;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   unsigned slot = 0, phase = 0;
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long p0 = tile * kTile;
-    const unsigned len = unsigned(min((long long)kTile, P.texels - p0));      // texels in this tile (multiple of 4)
+  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  for (int e = 0; e < P.epochs; ++e) {
+  unsigned local = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+    if (e > 0) {
+      // this tile was written by this CTA's consumers in epoch e-1: wait until every warp has stored (and fenced) it
+      const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
+      const unsigned need = (unsigned(e - 1) * my_tiles + local + publish_every) / publish_every * publish_every;
+      for (int w = 0; w < SH::kCW; ++w)
+        while (s_done[w] < need) {
+        }
+    }
+    const long long p0 = tile * SH::kTile;
+    const unsigned len = unsigned(min((long long)SH::kTile, P.texels - p0));      // texels in this tile (multiple of 4)
     auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
       // `planes` plane segments of `len` elements each, starting at element p0 of consecutive planes of `base`
       mbar_wait(&empty[slot], phase ^ 1);
-      unsigned dst = smem_u32(ring) + slot * unsigned(kSlotBytes);
+      unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
       const unsigned bar = smem_u32(&full[slot]);
       const unsigned seg = len * elem_bytes;
       mbar_expect_tx(&full[slot], seg * planes);
       const unsigned char* src = static_cast<const unsigned char*>(base) + size_t(p0) * elem_bytes;
       const size_t src_step = size_t(P.stride) * elem_bytes;
-      const unsigned dst_step = unsigned(kTile) * elem_bytes;
+      const unsigned dst_step = unsigned(SH::kTile) * elem_bytes;
       for (int j = 0; j < planes; ++j) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                      "r"(seg), "r"(bar)
@@ -600,66 +995,43 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
       fill(P.v, 4, 9);
     }
   }
+  }
 }
 
-template <int MODE, bool WANT_POW, int TGT>
-__global__ void __maxnreg__(SV_TILE_MAXNREG) tile_kernel(const Params P) {
+template <int MODE, bool WANT_POW, int TGT, typename SH>
+__global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: ring [slots * 9216] | barriers full[slots], empty[slots] | light geometry 2*N float4 | reduction scratch
   unsigned char* ring = smem;
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots) * kSlotBytes);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots) * SH::kSlotBytes);
   unsigned long long* empty = full + P.slots;
   float4* s_geo = reinterpret_cast<float4*>(empty + P.slots);
   float* stash = reinterpret_cast<float*>(s_geo + 2 * P.n_lights);
-  __shared__ float s_red[kConsumerWarps][4];
-  __shared__ double s_fin[256][4];
-  __shared__ bool s_last;
+  __shared__ unsigned s_done[SH::kCW];                              // per consumer warp: tiles stored (and fenced) so far
+  __shared__ float s_red[2][SH::kCW][4];
 
   const int tid = threadIdx.x;
+  if (tid < SH::kCW) s_done[tid] = 0u;
   if (tid == 0) {
     for (int s = 0; s < P.slots; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
+      mbar_init(&empty[s], SH::kCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  const bool coloc = stage_lights(P, s_geo, tid, kTileThreads);     // includes __syncthreads
+  const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (tid >= kTile) {
-    if (tid == kTile) tile_producer<MODE, TGT>(P, ring, full, empty);
+  if (tid >= SH::kConsumers) {
+    if (tid == SH::kConsumers) tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);
   } else {
-    if (coloc) tile_consumer<MODE, true, WANT_POW, TGT>(P, s_geo, ring, full, empty, stash, acc);
-    else tile_consumer<MODE, false, WANT_POW, TGT>(P, s_geo, ring, full, empty, stash, acc);
-  }
-
-  // ---- CTA partial -> global; the last CTA to finish reduces all partials (fixed order) ----
-  if (tid < kTile) {
-    warp_reduce4(acc);
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s_red[tid >> 5][c] = acc[c];
+    if (SH::kLanes == 2) {
+      if (coloc) tile_consumer2<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
+      else tile_consumer2<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
+    } else {
+      if (coloc) tile_consumer<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
+      else tile_consumer<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
     }
-  }
-  __syncthreads();
-  if (tid < 4) {
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < kConsumerWarps; ++w) a += s_red[w][tid];
-    __stcg(P.partials + (long long)blockIdx.x * 4 + tid, a);
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned ticket = atomicAdd(P.counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    finalize_block(P, int(gridDim.x), s_fin, tid, kTileThreads);
-    if (tid == 0) *P.counter = 0u;                         // leave the workspace ready for the next launch
   }
 }
 
@@ -726,6 +1098,7 @@ static Params base_params(const svbrdf_geom_t* g) {
   P.res_magic = ~0ull / (unsigned long long)g->res + 1ull;
   P.row_offset = g->row_offset;
   P.n_lights = g->n_lights;
+  P.epochs = 1;
   return P;
 }
 
@@ -733,8 +1106,9 @@ static inline int texel_blocks(const Params& P) { return int((P.texels + kThread
 
 // Workspace layout: [max(texel blocks, persistent CTAs)][4] floats of partials, then the finish counter.
 static inline size_t partial_rows(long long texels) {
-  const size_t tb = size_t((texels + kThreads - 1) / kThreads);
-  return tb > 4096 ? tb : 4096;
+  const size_t tb = size_t((texels + kThreads - 1) / kThreads);          // texel_kernel: one row per CTA
+  const size_t tile_rows = size_t(kMaxEpochs) * kRowsPerEpoch;             // tile_kernel: one row per warp and epoch
+  return tb > tile_rows ? tb : tile_rows;
 }
 
 struct Device {
@@ -751,7 +1125,30 @@ static int device_info(Device* d) {
 }
 
 template <int MODE, bool WANT_POW, int TGT>
+static int launch_texel_one(const Params& P, cudaStream_t st);
+
+// texel_kernel handles one epoch per launch: a multi-epoch request is unrolled on the host.
+template <int MODE, bool WANT_POW, int TGT>
 static int launch_texel(const Params& P, cudaStream_t st) {
+  if (P.epochs <= 1) {
+    Params Q = P;
+    Q.adam.step_size = P.step_size[0];
+    Q.adam.inv_sqrt_bc2 = P.inv_sqrt_bc2[0];
+    return launch_texel_one<MODE, WANT_POW, TGT>(Q, st);
+  }
+  for (int e = 0; e < P.epochs; ++e) {
+    Params Q = P;
+    Q.epochs = 1;
+    Q.adam.step_size = Q.step_size[0] = P.step_size[e];
+    Q.adam.inv_sqrt_bc2 = Q.inv_sqrt_bc2[0] = P.inv_sqrt_bc2[e];
+    Q.loss_out = P.loss_out ? P.loss_out + e : nullptr;
+    if (int err = launch_texel_one<MODE, WANT_POW, TGT>(Q, st)) return err;
+  }
+  return 0;
+}
+
+template <int MODE, bool WANT_POW, int TGT>
+static int launch_texel_one(const Params& P, cudaStream_t st) {
   const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
   auto kern = texel_kernel<MODE, WANT_POW, TGT>;
   if (smem > 48 * 1024) {
@@ -784,42 +1181,57 @@ static int env_int(const char* name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 
-template <int MODE, bool WANT_POW, int TGT>
-static int launch_tile(Params P, cudaStream_t st) {
-  if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+template <int MODE, bool WANT_POW, int TGT, typename SH>
+static int launch_tile_shape(Params P, cudaStream_t st) {
   const bool trace = env_int("SVBRDF_B200_TRACE", 0) != 0;
-  if (trace) fprintf(stderr, "[svbrdf] launch_tile mode %d texels %lld N %d\n", MODE, P.texels, P.n_lights);
   Device d;
   if (int e = device_info(&d)) return e;
   const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 1);
   const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
-  const size_t stash_bytes = SV_STASH ? size_t(kStashFloats) * kTile * 4 : 0;
+  const size_t stash_bytes = SV_STASH ? size_t(kStashFloats) * SH::kTile * 4 : 0;
   const size_t fixed = geo + stash_bytes + 64 + 2 * 8 * 64;            // barriers (<= 64 slots) + padding
-  const size_t static_smem = 9 * 1024;                                 // s_fin + s_red (static __shared__)
-  const size_t budget = size_t(228 * 1024) / ctas_per_sm - 1024 - static_smem;
+  const size_t static_smem = 1024;                                     // s_done + s_red (static __shared__)
+  const size_t budget = size_t(d.smem_optin + 1024) / ctas_per_sm - 1024 - static_smem;
   int slots = env_int("SVBRDF_B200_SLOTS", 0);
-  if (slots <= 0) slots = int((budget - fixed) / kSlotBytes);
+  if (slots <= 0) slots = int((budget - fixed) / SH::kSlotBytes);
   const int need = chunks_per_tile<MODE>(P.n_lights);
   if (slots > 2 * need) slots = 2 * need;                               // two whole tiles in flight is plenty
   if (slots > 64) slots = 64;
   if (slots < 2) return launch_texel<MODE, WANT_POW, TGT>(P, st);
   P.slots = slots;
-  const size_t smem = size_t(slots) * kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
+  const size_t smem = size_t(slots) * SH::kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
   if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
-  if (trace) fprintf(stderr, "[svbrdf] slots %d smem %zu sms %d optin %d\n", slots, smem, d.sms, d.smem_optin);
-  auto kern = tile_kernel<MODE, WANT_POW, TGT>;
+  auto kern = tile_kernel<MODE, WANT_POW, TGT, SH>;
   if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
   if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
-  if (trace) fprintf(stderr, "[svbrdf] attribute set\n");
-  const long long n_tiles = (P.texels + kTile - 1) / kTile;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   long long grid = (long long)d.sms * ctas_per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  P.counter = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
-  if (trace) fprintf(stderr, "[svbrdf] launching grid %lld\n", grid);
-  kern<<<int(grid), kTileThreads, smem, st>>>(P);
-  const int rc = int(cudaGetLastError());
-  if (trace) fprintf(stderr, "[svbrdf] launched rc %d\n", rc);
-  return rc;
+  P.counters = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
+  if (grid > kRowsPerEpoch) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (P.epochs > 1 && n_tiles / grid < 3) {                           // too few tiles per CTA for the lagging publication: one launch per epoch
+    Params Q = P;
+    for (int e = 0; e < P.epochs; ++e) {
+      Q.epochs = 1;
+      Q.step_size[0] = P.step_size[e];
+      Q.inv_sqrt_bc2[0] = P.inv_sqrt_bc2[e];
+      Q.loss_out = P.loss_out ? P.loss_out + e : nullptr;
+      if (int err = launch_tile_shape<MODE, WANT_POW, TGT, SH>(Q, st)) return err;
+    }
+    return 0;
+  }
+  if (trace) fprintf(stderr, "[svbrdf] tile_kernel mode %d lanes %d tile %d slots %d smem %zu grid %lld\n", MODE, SH::kLanes, SH::kTile, slots, smem, grid);
+  kern<<<int(grid), SH::kThreads, smem, st>>>(P);
+  return int(cudaGetLastError());
+}
+
+template <int MODE, bool WANT_POW, int TGT>
+static int launch_tile(Params P, cudaStream_t st) {
+  if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+#if SV_ENABLE_PACKED
+  if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
+#endif
+  return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 }
 
 template <int MODE>
@@ -853,7 +1265,7 @@ const char* svbrdf_error_string(int code) {
 
 size_t svbrdf_workspace_bytes(int32_t res, int32_t rows) {
   if (res <= 0 || rows <= 0) return 0;
-  return partial_rows((long long)res * rows) * 4 * sizeof(float) + 16;
+  return partial_rows((long long)res * rows) * 4 * sizeof(float) + kMaxEpochs * sizeof(unsigned) + 16;
 }
 
 int svbrdf_render_fwd(const svbrdf_geom_t* geom, const float* tex, float* out, svbrdf_stream_t stream) {
@@ -909,9 +1321,21 @@ int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v
   P.scale = float(l2_scale(geom, geom->n_lights));
   P.loss_norm = 1.0 / (double(geom->n_lights) * 3.0 * double(geom->res) * double(geom->res));
   P.pow_state = pow_state;
-  for (int e = 0; e < epochs; ++e) {
-    P.adam = make_adam(*adam, adam->step + e);
-    P.loss_out = loss_curve ? loss_curve + e : nullptr;
+  // optim_light couples all texels through light_pow every epoch -> one launch per epoch; otherwise up to
+  // kMaxEpochs epochs run inside one persistent launch.
+  const int per_launch = pow_state ? 1 : (env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs) < kMaxEpochs
+                                               ? (env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs) < 1 ? 1 : env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs))
+                                               : kMaxEpochs);
+  for (int e0 = 0; e0 < epochs; e0 += per_launch) {
+    const int n = epochs - e0 < per_launch ? epochs - e0 : per_launch;
+    for (int i = 0; i < n; ++i) {
+      const AdamStep<float> a = make_adam(*adam, adam->step + e0 + i);
+      if (i == 0) P.adam = a;
+      P.step_size[i] = a.step_size;
+      P.inv_sqrt_bc2[i] = a.inv_sqrt_bc2;
+    }
+    P.epochs = n;
+    P.loss_out = loss_curve ? loss_curve + e0 : nullptr;
     if (int err = launch_l2<kModeL2Adam>(P, pow_state != nullptr, target_dtype, stream)) return err;
   }
   return 0;

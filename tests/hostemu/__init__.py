@@ -59,12 +59,15 @@ def adam_scalars(step, lr, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def run(mode, tex, cam, light, power, size, res, io=None, dtype=np.float32, colocated=None, outer_clamp=False,
-        n_total=None, row0=0, m=None, v=None, adam=None, noise=False):
+        n_total=None, row0=0, m=None, v=None, adam=None, noise=False, packed=False):
     """Run the host emulation.  ``tex`` [9,H,W]; returns dict with out / grad_tex / grad_pow / loss.
 
     In MODE_ADAM ``tex``, ``m``, ``v`` are updated in place (pass arrays of ``dtype``).
     """
     fn = lib(noise).emu_run_f32 if dtype == np.float32 else lib(noise).emu_run_f64
+    if packed:                      # T = V2: the generic code instantiated for texel pairs (float only)
+        assert dtype == np.float32
+        fn = lib(noise).emu_run_v2
     keep_inplace = mode == MODE_ADAM
     tex_a = tex if keep_inplace else np.ascontiguousarray(tex, dtype=dtype)
     assert tex_a.dtype == dtype and tex_a.flags["C_CONTIGUOUS"]

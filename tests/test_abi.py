@@ -45,8 +45,9 @@ def test_abi_version_and_errors():
     assert L.svbrdf_error_string(0) == b"success"
     assert b"bad argument" in L.svbrdf_error_string(-1)
     assert b"unsupported" in L.svbrdf_error_string(-2)
-    assert L.svbrdf_workspace_bytes(1024, 1024) == (1024 * 1024 // 256) * 16 + 16      # block partials + finish counter
-    assert L.svbrdf_workspace_bytes(4096, 4096) == (4096 * 4096 // 256) * 16 + 16
+    # 64 epochs x 4096 rows of [loss, dpow x3] partials + 64 finish tickets (+ pad)
+    assert L.svbrdf_workspace_bytes(1024, 1024) == 64 * 4096 * 16 + 64 * 4 + 16
+    assert L.svbrdf_workspace_bytes(8192, 8192) == 64 * 4096 * 16 + 64 * 4 + 16
     assert L.svbrdf_workspace_bytes(0, 5) == 0
 
 

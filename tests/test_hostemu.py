@@ -92,3 +92,26 @@ def test_u8_division_is_correctly_rounded():
     resid = (b.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)      # fma(-q,255,b): exact in fp64
     fixed = (q.astype(np.float64) + resid.astype(np.float64) * np.float64(r)).astype(np.float32)
     assert np.array_equal(fixed, b / np.float32(255.0))
+
+
+@pytest.mark.parametrize("name", ["coloc_32x9", "edges_offaxis_32x9", "light_32x9"])
+def test_packed_pair_instantiation_equals_scalar(name):
+    """T = V2 (two texels per thread, what the packed FP32x2 CUDA kernel instantiates) gives the scalar float
+    results bit for bit on the host: the mask/select abstraction and the pair plumbing change no arithmetic."""
+    g = parity.golden(name)
+    a = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g))["out"]
+    b = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g), packed=True)["out"]
+    assert np.array_equal(a, b)
+    a = E.run(E.MODE_L2, g["tex0"][0], *_args(g, "power"), io=g["target"], outer_clamp=True)
+    b = E.run(E.MODE_L2, g["tex0"][0], *_args(g, "power"), io=g["target"], outer_clamp=True, packed=True)
+    assert np.array_equal(a["grad_tex"], b["grad_tex"]) and np.array_equal(a["grad_pow"], b["grad_pow"])
+    assert a["loss"] == pytest.approx(b["loss"], rel=1e-12)
+    a = E.run(E.MODE_VJP, np.clip(g["tex0"][0], -1, 1), *_args(g), io=g["grad_img"])
+    b = E.run(E.MODE_VJP, np.clip(g["tex0"][0], -1, 1), *_args(g), io=g["grad_img"], packed=True)
+    assert np.array_equal(a["grad_tex"], b["grad_tex"])
+    ta, tb = (np.array(g["tex0"][0], dtype=np.float32, copy=True) for _ in range(2))
+    ma, va, mb, vb = (np.zeros_like(ta) for _ in range(4))
+    for step in (1, 2, 3):
+        E.run(E.MODE_ADAM, ta, *_args(g, "power"), io=g["target"], outer_clamp=True, m=ma, v=va, adam=E.adam_scalars(step, 0.01))
+        E.run(E.MODE_ADAM, tb, *_args(g, "power"), io=g["target"], outer_clamp=True, m=mb, v=vb, adam=E.adam_scalars(step, 0.01), packed=True)
+    assert np.array_equal(ta, tb) and np.array_equal(va, vb)
