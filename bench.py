@@ -269,18 +269,37 @@ def run_b200_arm(args):
             ms = float(t.item())
         return ms
 
-    # ---- value: device-resident inputs, K fused steps (main kernel + loss finalize) ----
+    # ---- value: device-resident inputs, K steps (= epochs) of the optimisation loop.  As SvbrdfOptim.optim does,
+    # the epochs of one material are enqueued by ONE svbrdf_l2_adam_run call (up to 64 epochs per persistent launch);
+    # the K steps are dealt over the 4 materials so consecutive calls stream different data. ----
+    curve = th.zeros(max(K, 64), device=dev)
+    launches = [0]
+
+    def run_epochs(mat, epochs, first_step):
+        a = nv.Adam(LR, 0.9, 0.999, 1e-8, first_step)
+        nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(mat["tex"]), nv.ptr(mat["m"]), nv.ptr(mat["v"]), nv.ptr(mat["target"]), 0,
+                                      ctypes.byref(a), epochs, nv.ptr(curve), None, nv.ptr(ws), stream), "l2_adam_run")
+        launches[0] += (epochs + 63) // 64
+
+    share = [K // N_MATERIALS_CYCLED + (1 if i < K % N_MATERIALS_CYCLED else 0) for i in range(N_MATERIALS_CYCLED)]
+
+    def k_steps(_):
+        for i, ep in enumerate(share):
+            if ep:
+                run_epochs(mats[i], ep, 1 + W)
+
     for i in range(W):
         fused_step(mats[i % N_MATERIALS_CYCLED])
+    launches[0] = 0
     with ClockSampler(local) as clk:
-        ms = timed(lambda i: fused_step(mats[i % N_MATERIALS_CYCLED]), K)
+        ms = timed(k_steps, 1)
+    gpu_launches = launches[0]
     samples_per_step = P * n
     value = samples_per_step * world * K / (ms * 1e-3)
+    ms_k = ms / K                                          # mean time of one epoch inside the persistent launches
 
-    # ---- roofline: the dominant kernel alone (no loss finalize), same cycling ----
-    for i in range(3):
-        fused_step(mats[i % N_MATERIALS_CYCLED], with_loss=False)
-    ms_k = timed(lambda i: fused_step(mats[i % N_MATERIALS_CYCLED], with_loss=False), K) / K
+    # ---- the same K steps as K separate single-epoch launches (svbrdf_l2_adam_step), for comparison ----
+    ms_single = timed(lambda i: fused_step(mats[i % N_MATERIALS_CYCLED]), K) / K
     algo_bytes = (216 + 12 * n) * P
     peaks = {}
     try:
@@ -298,8 +317,9 @@ def run_b200_arm(args):
         pass
     achieved = algo_bytes / (ms_k * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "svbrdf::tile_kernel<kModeL2Adam> (persistent TMA-pipelined fused render+L2+backward+Adam)", "kernel_ms": ms_k,
-                "algorithmic_bytes_per_launch": algo_bytes, "bytes_per_texel": 216 + 12 * n, "peak_source": peak_src,
+                "kernel": "svbrdf::tile_kernel<kModeL2Adam> (persistent TMA-pipelined fused render+L2+backward+Adam)", "kernel_ms_per_epoch": ms_k,
+                "ms_per_epoch_single_epoch_launches": ms_single,
+                "algorithmic_bytes_per_epoch": algo_bytes, "bytes_per_texel": 216 + 12 * n, "peak_source": peak_src,
                 "samples_per_s_kernel_only": samples_per_step / (ms_k * 1e-3)}
 
     # ---- e2e: per step, upload that step's targets from pinned host memory, run, read the loss back ----
@@ -366,7 +386,8 @@ def run_b200_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "view_sharded": view, "clocks": clk.summary(),
-            "gpu_launches": K, "gpu_launches_what": "one tile_kernel<L2Adam> launch per step (loss reduction fused: last CTA finalises)",
+            "gpu_launches": gpu_launches,
+            "gpu_launches_what": "tile_kernel<L2Adam> launches in the timed region: one persistent launch per material and <=64 epochs (loss reduction fused: last CTA finalises each epoch)",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -375,38 +396,58 @@ def run_b200_arm(args):
 
 def view_sharded_bench(args, dev, world, rank, barrier):
     """Strong scaling of one material: `vs_res`^2 texels x `vs_lights` lights in total, lights sharded over the ranks
-    (SURVEY.md §8(e)); per epoch every rank runs svbrdf_l2_grad on its lights per row band, all-reduces the band
-    gradient over NCCL (overlapped with the next band's kernel) and applies the identical Adam update."""
+    (SURVEY.md §8(e)).  Two transports are timed on the same problem:
+      * "peer_push": the collective is fused into the kernels — svbrdf_l2_grad_push stores each tile's partial gradient
+        straight into the owner rank's slot over NVLink while shading, svbrdf_reduce_adam_push reduces + Adam-updates the
+        owned texels and stores the new parameters into every replica (N>1 only);
+      * "nccl": per row band svbrdf_l2_grad -> async NCCL all_reduce -> replicated svbrdf_adam_apply."""
     import torch.distributed as dist
-    import svbrdf_diff_renderer_b200 as pkg
     from svbrdf_diff_renderer_b200 import sharding, synth
     res, n = args.vs_res, args.vs_lights
     cl = synth.calibration(n)
-    vs = sharding.ViewShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev, bands=4)
     gt = synth.random_textures(res, 1).to(dev)
+    tex0 = synth.random_textures(res, 2)
+    epochs = 5
+    out = {"unit": UNIT, "scaling": "strong", "res": res, "lights_total": n, "epochs_timed": epochs,
+           "gradient_bytes_per_epoch": 9 * res * res * 4}
+
+    def time_optim(opt):
+        opt.optim(2, LR)                                 # warm-up (NCCL channels / symmetric-memory barriers, kernels)
+        barrier()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        losses = opt.optim(epochs, LR)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = th.tensor([ms], device=dev, dtype=th.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return {"value": res * res * n * epochs / (ms * 1e-3), "ms_per_epoch": ms / epochs, "loss_first_last": [losses[0], losses[-1]]}
+
+    vs = sharding.ViewShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev, bands=4)
     with th.no_grad():                                   # this rank's targets only
         tgt = vs.renderer.eval(gt)
     vs.load_targets(tgt)
-    del tgt
-    vs.init_from_tex(synth.random_textures(res, 2))
-    vs.optim(2, LR)                                      # warm-up (NCCL channels, kernels)
-    epochs = 5
-    barrier()
-    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    e0.record()
-    losses = vs.optim(epochs, LR)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    vs.init_from_tex(tex0)
+    out["lights_per_gpu"] = vs.n_local
+    out["nccl"] = time_optim(vs)
+    out["nccl"]["what"] = ("4 row bands: svbrdf_l2_grad -> async NCCL all_reduce(SUM) of the band gradient (overlaps the next band) -> "
+                           "replicated svbrdf_adam_apply") if world > 1 else "1 GPU: svbrdf_l2_grad + svbrdf_adam_apply per band, no collective"
+    del vs
     if world > 1:
-        t = th.tensor([ms], device=dev, dtype=th.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    samples = res * res * n * epochs
-    return {"value": samples / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "ms_per_epoch": ms / epochs, "res": res, "lights_total": n,
-            "lights_per_gpu": vs.n_local, "bands": len(vs.bands), "allreduce_bytes_per_epoch": 9 * res * res * 4,
-            "collective": "NCCL all_reduce(SUM) of the [9,rows,R] band gradients, async, overlapped with the next band's kernel" if world > 1 else "none (1 GPU)",
-            "loss_first_last": [losses[0], losses[-1]]}
+        ps = sharding.PeerShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev)
+        ps.load_targets(tgt)
+        ps.init_from_tex(tex0)
+        out["peer_push"] = time_optim(ps)
+        out["peer_push"]["what"] = ("svbrdf_l2_grad_push (reduce-scatter fused into the gradient kernel: peer stores over NVLink) -> barrier -> "
+                                    "svbrdf_reduce_adam_push (owner-side reduce + sharded Adam + all-gather by peer stores) -> barrier")
+        del ps
+    best = max((out[k] for k in ("nccl", "peer_push") if k in out), key=lambda d: d["value"])
+    out["value"] = best["value"]
+    out["ms_per_epoch"] = best["ms_per_epoch"]
+    return out
 
 
 def main():

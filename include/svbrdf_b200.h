@@ -106,6 +106,32 @@ int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v
                        int32_t target_dtype, const svbrdf_adam_t* adam, int32_t epochs, float* loss_curve,
                        float* pow_state, void* workspace, svbrdf_stream_t stream);
 
+/* ---- view-sharded runs over NVLink peer memory (one process per GPU, <= 8 GPUs of one NVSwitch box) ----
+ * Texel p is OWNED by rank p / chunk (chunk: a multiple of 480 texels).  Every rank maps every peer's buffers
+ * (CUDA IPC / torch symmetric memory); the pointers below are peer-mapped DEVICE pointers, index = rank.
+ *   recv[o]: rank o's receive buffer  [world, 9, chunk]  — slot [r] takes rank r's partial gradient of o's texels
+ *   tex[q] : rank q's replica of the textures [9, texels]                                                     */
+typedef struct svbrdf_peers_t {
+  int32_t world, rank;
+  int64_t chunk;
+  float* recv[8];
+  float* tex[8];
+} svbrdf_peers_t;
+
+/* svbrdf_l2_grad fused with the reduce-scatter: the partial gradient of every tile is STORED STRAIGHT INTO THE
+ * OWNER'S receive slot over NVLink while the next tile is being shaded (no local gradient tensor, no NCCL call).
+ * `tex` is this rank's replica (peers->tex[peers->rank]); geom holds this rank's light shard; full image only. */
+int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void* target, int32_t target_dtype,
+                        int32_t n_total, const svbrdf_peers_t* peers, float* loss_out, void* workspace,
+                        svbrdf_stream_t stream);
+
+/* After all ranks' pushes have landed (cross-rank barrier): for the texels this rank owns, sum the `world`
+ * partial gradients in rank order (deterministic, every texel reduced exactly once => replicas stay bit-identical),
+ * apply torch.optim.Adam.step (m, v: [9, chunk], owner-local) and store the new parameters into EVERY rank's
+ * replica (all-gather by peer stores).  texels = res*res. */
+int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* m, float* v, const svbrdf_adam_t* adam,
+                            svbrdf_stream_t stream);
+
 /* torch.optim.Adam.step on a flat fp32 array (adam.py:531-547), used after the gradient
  * all-reduce of a view-sharded run. */
 int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,

@@ -35,6 +35,7 @@ TARGET_F32, TARGET_U8 = 0, 1
 EXPORTS = (
     "svbrdf_abi_version", "svbrdf_error_string", "svbrdf_workspace_bytes", "svbrdf_render_fwd", "svbrdf_render_bwd",
     "svbrdf_l2_grad", "svbrdf_l2_adam_step", "svbrdf_l2_adam_run", "svbrdf_adam_apply",
+    "svbrdf_l2_grad_push", "svbrdf_reduce_adam_push",
 )
 
 
@@ -45,6 +46,12 @@ class Geom(ctypes.Structure):
         ("size", ctypes.c_float), ("res", ctypes.c_int32), ("rows", ctypes.c_int32), ("row_offset", ctypes.c_int32),
         ("n_lights", ctypes.c_int32), ("plane_stride", ctypes.c_int64),
     ]
+
+
+class Peers(ctypes.Structure):
+    """``svbrdf_peers_t``."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("chunk", ctypes.c_int64),
+                ("recv", ctypes.c_void_p * 8), ("tex", ctypes.c_void_p * 8)]
 
 
 class Adam(ctypes.Structure):
@@ -112,6 +119,9 @@ def lib() -> ctypes.CDLL:
     L.svbrdf_l2_adam_step.argtypes = [gp, vp, vp, vp, vp, i32, ap, vp, vp, vp, vp]
     L.svbrdf_l2_adam_run.argtypes = [gp, vp, vp, vp, vp, i32, ap, i32, vp, vp, vp, vp]
     L.svbrdf_adam_apply.argtypes = [vp, vp, vp, vp, ctypes.c_size_t, ap, vp]
+    pp = ctypes.POINTER(Peers)
+    L.svbrdf_l2_grad_push.argtypes = [gp, vp, vp, i32, i32, pp, vp, vp, vp]
+    L.svbrdf_reduce_adam_push.argtypes = [pp, i64, vp, vp, ap, vp]
     for name in EXPORTS[3:]:
         getattr(L, name).restype = ctypes.c_int
     if L.svbrdf_abi_version() != 1:

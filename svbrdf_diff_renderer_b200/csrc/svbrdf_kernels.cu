@@ -123,6 +123,11 @@ struct Params {
   int epochs;
   float step_size[64];
   float inv_sqrt_bc2[64];
+  // view-sharded push mode (svbrdf_l2_grad_push): gradients go to the owner's receive slot in peer memory
+  int push_world;         // 0 = off
+  int push_rank;
+  long long push_chunk;   // texels owned per rank (multiple of the tile size)
+  float* push_recv[8];    // peer-mapped receive buffers [world, 9, chunk]
 };
 constexpr int kMaxEpochs = 64;          // per launch
 constexpr int kRowsPerEpoch = 4096;     // workspace rows ([loss, gpow x3]) per epoch: one per consumer warp
@@ -419,6 +424,11 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
         P.m[idx] = mk;
         P.v[idx] = vk;
       }
+    } else if (MODE == kModeL2Grad && P.push_world > 0) {
+      const long long owner = p / P.push_chunk;
+      float* po = P.push_recv[owner] + (size_t(P.push_rank) * 9) * P.push_chunk + (p - owner * P.push_chunk);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) po[k * P.push_chunk] = gt[k];
     } else {
 #pragma unroll
       for (int k = 0; k < 9; ++k) P.out[k * P.stride + p] = gt[k];
@@ -685,11 +695,21 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         }
       }
     } else if (valid) {
-      float* __restrict__ po = P.out + p;
+      float* __restrict__ po;
+      long long ostride;
+      if (MODE == kModeL2Grad && P.push_world > 0) {
+        // reduce-scatter by push: this tile belongs to rank `owner`; write our partial into its slot [push_rank]
+        const long long owner = (tile * SH::kTile) / P.push_chunk;        // uniform per tile (chunk % tile == 0)
+        po = P.push_recv[owner] + (size_t(P.push_rank) * 9) * P.push_chunk + (p - owner * P.push_chunk);
+        ostride = P.push_chunk;
+      } else {
+        po = P.out + p;
+        ostride = P.stride;
+      }
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         *po = gt[k];
-        po += P.stride;
+        po += ostride;
       }
     }
     if (valid) {
@@ -1035,6 +1055,46 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
   }
 }
 
+// View-sharded push mode, second half: owner-side reduction of the `world` partial gradients (fixed rank order),
+// Adam on the owned texels, new parameters stored into every rank's replica over NVLink (all-gather by push).
+struct PushAdamParams {
+  int world, rank;
+  long long chunk, texels;
+  const float* recv;      // this rank's receive buffer [world, 9, chunk]
+  float* tex[8];          // peer-mapped replicas [9, texels]
+  float* m;               // [9, chunk]
+  float* v;
+  AdamStep<float> adam;
+};
+
+__global__ void __launch_bounds__(256) reduce_adam_push_kernel(const PushAdamParams Q) {
+  const long long first = (long long)Q.rank * Q.chunk;
+  long long owned = Q.texels - first;
+  if (owned > Q.chunk) owned = Q.chunk;
+  if (owned <= 0) return;
+  const long long n4 = owned / 4;                           // chunk, texels are multiples of 4
+  const long long total = n4 * 9;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long k = idx / n4, i4 = idx - k * n4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < Q.world; ++r) {                     // fixed order: deterministic, identical on every rank
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(Q.recv + (size_t(r) * 9 + k) * Q.chunk) + i4);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    float4* pm = reinterpret_cast<float4*>(Q.m + k * Q.chunk) + i4;
+    float4* pv = reinterpret_cast<float4*>(Q.v + k * Q.chunk) + i4;
+    const size_t toff = size_t(k) * Q.texels + first;
+    float4 p4 = reinterpret_cast<const float4*>(Q.tex[Q.rank] + toff)[i4], m4 = *pm, v4 = *pv;
+    adam_update(p4.x, m4.x, v4.x, g.x, Q.adam);
+    adam_update(p4.y, m4.y, v4.y, g.y, Q.adam);
+    adam_update(p4.z, m4.z, v4.z, g.z, Q.adam);
+    adam_update(p4.w, m4.w, v4.w, g.w, Q.adam);
+    *pm = m4;
+    *pv = v4;
+    for (int q = 0; q < Q.world; ++q) reinterpret_cast<float4*>(Q.tex[q] + toff)[i4] = p4;    // own replica + peers
+  }
+}
+
 __global__ void __launch_bounds__(256) adam_apply_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                          const float* __restrict__ g, size_t n, const AdamStep<float> a) {
   const size_t n4 = n / 4;
@@ -1345,6 +1405,55 @@ int svbrdf_l2_adam_step(const svbrdf_geom_t* geom, float* tex, float* m, float* 
                         const svbrdf_adam_t* adam, float* loss_out, float* pow_state, void* workspace,
                         svbrdf_stream_t stream) {
   return svbrdf_l2_adam_run(geom, tex, m, v, target, target_dtype, adam, 1, loss_out, pow_state, workspace, stream);
+}
+
+static int check_peers(const svbrdf_peers_t* p) {
+  if (!p || p->world < 1 || p->world > 8 || p->rank < 0 || p->rank >= p->world || p->chunk <= 0 || p->chunk % 480 != 0) return SVBRDF_E_BADARG;
+  for (int r = 0; r < p->world; ++r)
+    if (!p->recv[r] || !p->tex[r]) return SVBRDF_E_BADARG;
+  return 0;
+}
+
+int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void* target, int32_t target_dtype, int32_t n_total,
+                        const svbrdf_peers_t* peers, float* loss_out, void* workspace, svbrdf_stream_t stream) {
+  if (int e = check_geom(geom)) return e;
+  if (int e = check_peers(peers)) return e;
+  if (!tex || !target || !workspace || n_total < geom->n_lights || geom->rows != geom->res || geom->row_offset != 0) return SVBRDF_E_BADARG;
+  if ((long long)peers->world * peers->chunk < (long long)geom->res * geom->res) return SVBRDF_E_BADARG;
+  Params P = base_params(geom);
+  P.tex = const_cast<float*>(tex);
+  P.io = target;
+  P.out = nullptr;
+  P.partials = static_cast<float*>(workspace);
+  P.scale = float(l2_scale(geom, n_total));
+  P.loss_norm = 1.0 / (double(n_total) * 3.0 * double(geom->res) * double(geom->res));
+  P.loss_out = loss_out;
+  P.push_world = peers->world;
+  P.push_rank = peers->rank;
+  P.push_chunk = peers->chunk;
+  for (int r = 0; r < peers->world; ++r) P.push_recv[r] = peers->recv[r];
+  return launch_l2<kModeL2Grad>(P, false, target_dtype, stream);
+}
+
+int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* m, float* v, const svbrdf_adam_t* adam,
+                            svbrdf_stream_t stream) {
+  if (int e = check_peers(peers)) return e;
+  if (!m || !v || !adam || adam->step < 1 || texels <= 0 || texels % 4 != 0) return SVBRDF_E_BADARG;
+  PushAdamParams Q{};
+  Q.world = peers->world;
+  Q.rank = peers->rank;
+  Q.chunk = peers->chunk;
+  Q.texels = texels;
+  Q.recv = peers->recv[peers->rank];
+  for (int r = 0; r < peers->world; ++r) Q.tex[r] = peers->tex[r];
+  Q.m = m;
+  Q.v = v;
+  Q.adam = make_adam(*adam, adam->step);
+  const long long work = peers->chunk / 4 * 9;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  reduce_adam_push_kernel<<<int(blocks), 256, 0, stream>>>(Q);
+  return int(cudaGetLastError());
 }
 
 int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,

@@ -157,6 +157,105 @@ class ViewShardedOptim:
         return self.losses
 
 
+class PeerShardedOptim:
+    """View-sharded optimisation with the collective fused into the kernels over NVLink peer memory.
+
+    Same partitioning as ``ViewShardedOptim`` (contiguous light shards, replicated textures, global MSE normaliser)
+    but no NCCL call on the data path.  Per epoch:
+
+    1. ``svbrdf_l2_grad_push`` — the persistent gradient kernel stores each tile's partial gradient straight into
+       the receive slot of the rank that OWNS the tile (texel ``p`` belongs to rank ``p // chunk``), i.e. the
+       reduce-scatter traffic leaves over NVLink while the next tiles are being shaded;
+    2. a cross-rank barrier (symmetric-memory signal pads, on the stream);
+    3. ``svbrdf_reduce_adam_push`` — every rank sums the ``world`` partials of ITS texels in rank order, applies Adam
+       to them (``m``/``v`` exist only for owned texels: 1/world of the optimiser state and work) and stores the new
+       parameters into every rank's replica (all-gather by peer stores);
+    4. a second barrier.
+
+    Every texel is reduced and updated on exactly one rank, so the replicas are bit-identical by construction.
+    Buffers come from ``torch.distributed._symmetric_memory`` (CUDA VMM handles exchanged at rendezvous); PyTorch
+    only allocates and exchanges pointers — all arithmetic and all data movement is in the two kernels.
+    """
+
+    TILE = 480      # ownership granularity = tile size of the gradient kernel (include/svbrdf_b200.h)
+
+    def __init__(self, res, n_total, size, cl, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as nv
+        from .microfacet import Microfacet
+        if not dist.is_initialized():
+            raise RuntimeError("PeerShardedOptim needs an initialised process group (NCCL, one process per GPU)")
+        self.nv, self.symm = nv, symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("peer-push mode covers one NVSwitch box: at most 8 ranks")
+        self.res, self.n_total, self.size, self.device = res, n_total, float(size), th.device(device)
+        self.start, self.end = split_range(n_total, self.world, self.rank)
+        self.n_local = self.end - self.start
+        if self.n_local < 1:
+            raise RuntimeError(f"rank {self.rank}: no lights to own")
+        self.renderer = Microfacet(res, self.n_local, size,
+                                   [cl[0][self.start:self.end].to(self.device), cl[1][self.start:self.end].to(self.device), cl[2].to(self.device)],
+                                   self.device)
+        self.texels = res * res
+        per = -(-self.texels // self.world)
+        self.chunk = -(-per // self.TILE) * self.TILE
+        name = self.group.group_name
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(name)
+            except Exception:
+                pass
+        self.tex_sym = symm.empty(9 * self.texels, dtype=th.float32, device=self.device)
+        self.recv_sym = symm.empty(self.world * 9 * self.chunk, dtype=th.float32, device=self.device)
+        self.h_tex = symm.rendezvous(self.tex_sym, name)
+        self.h_recv = symm.rendezvous(self.recv_sym, name)
+        self.peers = nv.Peers(self.world, self.rank, self.chunk)
+        for r in range(self.world):
+            self.peers.recv[r] = int(self.h_recv.buffer_ptrs[r])
+            self.peers.tex[r] = int(self.h_tex.buffer_ptrs[r])
+        self.ws = nv.workspace(res, res, self.device)
+        self.losses = []
+
+    def load_targets(self, local_targets):
+        if tuple(local_targets.shape) != (self.n_local, 3, self.res, self.res):
+            raise RuntimeError(f"rank {self.rank}: targets must be [{self.n_local},3,{self.res},{self.res}]")
+        self.targets = local_targets.to(self.device).contiguous()
+
+    def init_from_tex(self, textures):
+        full = textures.detach().to(device=self.device, dtype=th.float32).contiguous().clone()
+        dist.broadcast(full, src=dist.get_global_rank(self.group, 0), group=self.group)
+        self.tex_sym.copy_(full.view(-1))
+        th.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    @property
+    def textures(self):
+        return self.tex_sym.view(1, 9, self.res, self.res)
+
+    def optim(self, epochs, lr):
+        nv, L = self.nv, self.nv.lib()
+        m = th.zeros(9 * self.chunk, dtype=th.float32, device=self.device)
+        v = th.zeros_like(m)
+        curve = th.zeros(max(epochs, 1), dtype=th.float32, device=self.device)
+        geom = self.renderer._geom(self.renderer._pow)
+        stream = nv.stream_ptr(self.device)
+        for epoch in range(epochs):
+            nv.check(L.svbrdf_l2_grad_push(ctypes.byref(geom), nv.ptr(self.tex_sym), nv.ptr(self.targets), nv.target_dtype_code(self.targets),
+                                           self.n_total, ctypes.byref(self.peers), ctypes.c_void_p(curve.data_ptr() + 4 * epoch), nv.ptr(self.ws),
+                                           stream), "svbrdf_l2_grad_push")
+            self.h_recv.barrier(channel=0)                  # every rank's partials have landed
+            a = nv.Adam(float(lr), 0.9, 0.999, 1e-8, epoch + 1)
+            nv.check(L.svbrdf_reduce_adam_push(ctypes.byref(self.peers), self.texels, nv.ptr(m), nv.ptr(v), ctypes.byref(a), stream),
+                     "svbrdf_reduce_adam_push")
+            self.h_tex.barrier(channel=0)                   # every replica holds the new parameters
+        if epochs > 0:
+            dist.all_reduce(curve, op=dist.ReduceOp.SUM, group=self.group)      # loss shares add; once per run
+        self.losses = curve[:epochs].tolist()
+        return self.losses
+
+
 def optimise_materials(n_materials, make_problem, epochs, lr, device, group=None):
     """Material-sharded driver: ``make_problem(i)`` -> ``(renderer, targets, start_textures)`` for material i.
 

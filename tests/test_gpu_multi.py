@@ -54,6 +54,12 @@ def _nccl_worker(rank, world, port, out):
         vs.load_targets(T(g["target"], dev)[vs.start:vs.end])
         vs.init_from_tex(T(g["tex0"], dev))
         losses = vs.optim(int(g["epochs"]), float(g["lr"]))
+        # the same problem with the collective fused into the kernels (peer stores over NVLink, no NCCL on the data path)
+        ps = sharding.PeerShardedOptim(24, 16, float(g["size"]), cl, dev)
+        ps.load_targets(T(g["target"], dev)[ps.start:ps.end])
+        ps.init_from_tex(T(g["tex0"], dev))
+        p2p_losses = ps.optim(int(g["epochs"]), float(g["lr"]))
+        p2p_tex = ps.textures.clone().cpu()
         # material-sharded: 5 small materials
         def make(i):
             r = pkg.Microfacet(32, 9, synth.IM_SIZE_CM, [c.to(dev) for c in synth.calibration(9)], dev)
@@ -61,7 +67,8 @@ def _nccl_worker(rank, world, port, out):
                 tgt = r.eval(synth.random_textures(32, 100 + i).to(dev))
             return r, tgt, synth.random_textures(32, 200 + i).to(dev)
         mine, all_losses = sharding.optimise_materials(5, make, 5, 0.01, dev)
-        th.save({"losses": losses, "tex": vs.textures.cpu(), "mine": sorted(mine), "all": all_losses}, f"{out}/r{rank}.pt")
+        th.save({"losses": losses, "tex": vs.textures.cpu(), "mine": sorted(mine), "all": all_losses, "p2p_losses": p2p_losses, "p2p_tex": p2p_tex},
+                f"{out}/r{rank}.pt")
     finally:
         dist.destroy_process_group()
 
@@ -75,6 +82,11 @@ def test_two_rank_nccl_view_and_material_sharding(tmp_path):
     assert th.equal(a["tex"], b["tex"]) and a["losses"] == b["losses"]          # replicas stay bit-identical
     np.testing.assert_allclose(np.array(a["losses"]), g["loss_f64"], rtol=5e-5)
     parity.check_against_arbiter(a["tex"].numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "2-rank view-sharded maps",
+                                 floor=2e-4, min_fraction=0.998)
+    # peer-push mode: replicas bit-identical by construction, same optimisation as the NCCL mode
+    assert th.equal(a["p2p_tex"], b["p2p_tex"]) and a["p2p_losses"] == b["p2p_losses"]
+    np.testing.assert_allclose(np.array(a["p2p_losses"]), g["loss_f64"], rtol=5e-5)
+    parity.check_against_arbiter(a["p2p_tex"].numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "2-rank peer-push maps",
                                  floor=2e-4, min_fraction=0.998)
     assert a["mine"] == [0, 2, 4] and b["mine"] == [1, 3]
     assert a["all"] == b["all"] and len(a["all"]) == 5 and all(np.isfinite(a["all"]))
