@@ -442,8 +442,10 @@ def view_sharded_bench(args, dev, world, rank, barrier):
         ps.load_targets(tgt)
         ps.init_from_tex(tex0)
         out["peer_push"] = time_optim(ps)
-        out["peer_push"]["what"] = ("svbrdf_l2_grad_push (reduce-scatter fused into the gradient kernel: peer stores over NVLink) -> barrier -> "
-                                    "svbrdf_reduce_adam_push (owner-side reduce + sharded Adam + all-gather by peer stores) -> barrier")
+        out["peer_push"]["pull_textures_from_owner"] = bool(ps.pull)
+        out["peer_push"]["what"] = ("svbrdf_l2_grad_push (TMA-loads each tile's textures from the owner's replica over NVLink, stores the partial "
+                                    "gradient into the owner's slot: all-gather and reduce-scatter fused into the gradient kernel) -> barrier -> "
+                                    "svbrdf_reduce_adam_push (owner-side reduce + sharded Adam, local) -> barrier")
         del ps
     best = max((out[k] for k in ("nccl", "peer_push") if k in out), key=lambda d: d["value"])
     out["value"] = best["value"]

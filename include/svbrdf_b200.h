@@ -116,6 +116,11 @@ typedef struct svbrdf_peers_t {
   int64_t chunk;
   float* recv[8];
   float* tex[8];
+  float* tex_multicast; /* optional NVSwitch multicast mapping of the tex replicas (NVLS); NULL = unicast peer stores */
+  int32_t pull_tex;     /* 1: no all-gather at all — the gradient kernel TMA-loads each tile's textures from the OWNER's
+                           replica over NVLink (hidden by the shared-memory ring) and svbrdf_reduce_adam_push stores the
+                           new parameters only into the owner's replica; a rank's replica is then authoritative only for
+                           the texels it owns */
 } svbrdf_peers_t;
 
 /* svbrdf_l2_grad fused with the reduce-scatter: the partial gradient of every tile is STORED STRAIGHT INTO THE
@@ -128,7 +133,8 @@ int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void*
 /* After all ranks' pushes have landed (cross-rank barrier): for the texels this rank owns, sum the `world`
  * partial gradients in rank order (deterministic, every texel reduced exactly once => replicas stay bit-identical),
  * apply torch.optim.Adam.step (m, v: [9, chunk], owner-local) and store the new parameters into EVERY rank's
- * replica (all-gather by peer stores).  texels = res*res. */
+ * replica (all-gather by peer stores; with peers->tex_multicast one multimem.st per value, replicated by the switch).
+ * texels = res*res. */
 int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* m, float* v, const svbrdf_adam_t* adam,
                             svbrdf_stream_t stream);
 

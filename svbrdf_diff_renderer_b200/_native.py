@@ -51,7 +51,8 @@ class Geom(ctypes.Structure):
 class Peers(ctypes.Structure):
     """``svbrdf_peers_t``."""
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("chunk", ctypes.c_int64),
-                ("recv", ctypes.c_void_p * 8), ("tex", ctypes.c_void_p * 8)]
+                ("recv", ctypes.c_void_p * 8), ("tex", ctypes.c_void_p * 8), ("tex_multicast", ctypes.c_void_p),
+                ("pull_tex", ctypes.c_int32)]
 
 
 class Adam(ctypes.Structure):

@@ -128,6 +128,8 @@ struct Params {
   int push_rank;
   long long push_chunk;   // texels owned per rank (multiple of the tile size)
   float* push_recv[8];    // peer-mapped receive buffers [world, 9, chunk]
+  const float* push_tex[8];  // pull mode: every rank's texture replica; a tile is read from its owner's (nullable)
+  int push_pull;
 };
 constexpr int kMaxEpochs = 64;          // per launch
 constexpr int kRowsPerEpoch = 4096;     // workspace rows ([loss, gpow x3]) per epoch: one per consumer warp
@@ -392,8 +394,10 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
 
   float raw[9], t[9];
   bool outer[9];
+  const float* tex_src = P.tex;
+  if (MODE == kModeL2Grad && P.push_pull) tex_src = P.push_tex[pc / P.push_chunk];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) raw[k] = (MODE == kModeL2Adam) ? P.tex[k * P.stride + pc] : __ldg(P.tex + k * P.stride + pc);
+  for (int k = 0; k < 9; ++k) raw[k] = (MODE == kModeL2Adam) ? P.tex[k * P.stride + pc] : __ldg(tex_src + k * P.stride + pc);
   clamp_outer<MODE>(raw, t, outer);
   Texel<float> tx;
   TexelAux<float> ax;
@@ -1005,7 +1009,10 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
       }
       advance();
     };
-    fill(P.tex, 4, 9);
+    // view-sharded pull mode: the owner's replica is the authoritative copy of this tile's textures
+    const float* tex_src = P.tex;
+    if (MODE == kModeL2Grad && P.push_pull) tex_src = P.push_tex[p0 / P.push_chunk];
+    fill(tex_src, 4, 9);
     for (int i0 = 0; i0 < N; i0 += kChunkLights) {
       const int nl = min(kChunkLights, N - i0);
       fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
@@ -1062,6 +1069,8 @@ struct PushAdamParams {
   long long chunk, texels;
   const float* recv;      // this rank's receive buffer [world, 9, chunk]
   float* tex[8];          // peer-mapped replicas [9, texels]
+  float* tex_mc;          // NVSwitch multicast mapping of the replicas (nullable)
+  int local_only;         // pull mode: peers read the owner's replica themselves
   float* m;               // [9, chunk]
   float* v;
   AdamStep<float> adam;
@@ -1091,7 +1100,16 @@ __global__ void __launch_bounds__(256) reduce_adam_push_kernel(const PushAdamPar
     adam_update(p4.w, m4.w, v4.w, g.w, Q.adam);
     *pm = m4;
     *pv = v4;
-    for (int q = 0; q < Q.world; ++q) reinterpret_cast<float4*>(Q.tex[q] + toff)[i4] = p4;    // own replica + peers
+    if (Q.local_only) {
+      reinterpret_cast<float4*>(Q.tex[Q.rank] + toff)[i4] = p4;
+    } else if (Q.tex_mc) {
+      // one store, replicated to every GPU's replica by the NVSwitch (NVLS multicast)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float4*>(Q.tex_mc + toff) + i4),
+                   "f"(p4.x), "f"(p4.y), "f"(p4.z), "f"(p4.w)
+                   : "memory");
+    } else {
+      for (int q = 0; q < Q.world; ++q) reinterpret_cast<float4*>(Q.tex[q] + toff)[i4] = p4;    // own replica + peers
+    }
   }
 }
 
@@ -1431,7 +1449,11 @@ int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void*
   P.push_world = peers->world;
   P.push_rank = peers->rank;
   P.push_chunk = peers->chunk;
-  for (int r = 0; r < peers->world; ++r) P.push_recv[r] = peers->recv[r];
+  for (int r = 0; r < peers->world; ++r) {
+    P.push_recv[r] = peers->recv[r];
+    P.push_tex[r] = peers->tex[r];
+  }
+  P.push_pull = peers->pull_tex ? 1 : 0;
   return launch_l2<kModeL2Grad>(P, false, target_dtype, stream);
 }
 
@@ -1446,6 +1468,8 @@ int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* 
   Q.texels = texels;
   Q.recv = peers->recv[peers->rank];
   for (int r = 0; r < peers->world; ++r) Q.tex[r] = peers->tex[r];
+  Q.tex_mc = peers->tex_multicast;
+  Q.local_only = peers->pull_tex ? 1 : 0;
   Q.m = m;
   Q.v = v;
   Q.adam = make_adam(*adam, adam->step);

@@ -179,7 +179,7 @@ class PeerShardedOptim:
 
     TILE = 480      # ownership granularity = tile size of the gradient kernel (include/svbrdf_b200.h)
 
-    def __init__(self, res, n_total, size, cl, device, group=None):
+    def __init__(self, res, n_total, size, cl, device, group=None, multicast=True, pull=True):
         import torch.distributed._symmetric_memory as symm
         from . import _native as nv
         from .microfacet import Microfacet
@@ -215,6 +215,18 @@ class PeerShardedOptim:
         for r in range(self.world):
             self.peers.recv[r] = int(self.h_recv.buffer_ptrs[r])
             self.peers.tex[r] = int(self.h_tex.buffer_ptrs[r])
+        # NVSwitch multicast (NVLS): one multimem.st replaces `world` peer stores in the all-gather
+        mc = 0
+        try:
+            if multicast and self.h_tex.has_multicast_support(self.device.type, self.device.index):
+                mc = int(self.h_tex.multicast_ptr or 0)
+        except Exception:
+            mc = 0
+        self.multicast = mc != 0
+        self.peers.tex_multicast = mc if mc else None
+        # pull mode (default): no all-gather — the gradient kernel reads each tile's textures from its owner over NVLink
+        self.pull = bool(pull)
+        self.peers.pull_tex = 1 if self.pull else 0
         self.ws = nv.workspace(res, res, self.device)
         self.losses = []
 
@@ -232,7 +244,19 @@ class PeerShardedOptim:
 
     @property
     def textures(self):
-        return self.tex_sym.view(1, 9, self.res, self.res)
+        """Current maps ``[1,9,R,R]``.  In pull mode a replica is authoritative only for the texels its rank owns, so
+        the owned chunks are gathered (one collective, outside the optimisation loop)."""
+        full = self.tex_sym.view(9, self.texels)
+        if not self.pull:
+            return full.view(1, 9, self.res, self.res)
+        mine = th.zeros(9, self.chunk, dtype=th.float32, device=self.device)
+        lo = self.rank * self.chunk
+        hi = min(lo + self.chunk, self.texels)
+        if hi > lo:
+            mine[:, :hi - lo] = full[:, lo:hi]
+        parts = [th.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        return th.cat(parts, 1)[:, :self.texels].reshape(1, 9, self.res, self.res).contiguous()
 
     def optim(self, epochs, lr):
         nv, L = self.nv, self.nv.lib()

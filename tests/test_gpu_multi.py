@@ -60,6 +60,15 @@ def _nccl_worker(rank, world, port, out):
         ps.init_from_tex(T(g["tex0"], dev))
         p2p_losses = ps.optim(int(g["epochs"]), float(g["lr"]))
         p2p_tex = ps.textures.clone().cpu()
+        mc_used = ps.multicast
+        assert ps.pull
+        # and once more with the push all-gather (unicast peer stores) instead of pulling tiles from their owner
+        pu = sharding.PeerShardedOptim(24, 16, float(g["size"]), cl, dev, multicast=False, pull=False)
+        pu.load_targets(T(g["target"], dev)[pu.start:pu.end])
+        pu.init_from_tex(T(g["tex0"], dev))
+        pu.optim(int(g["epochs"]), float(g["lr"]))
+        assert not pu.multicast
+        uni_tex = pu.textures.clone().cpu()
         # material-sharded: 5 small materials
         def make(i):
             r = pkg.Microfacet(32, 9, synth.IM_SIZE_CM, [c.to(dev) for c in synth.calibration(9)], dev)
@@ -67,7 +76,8 @@ def _nccl_worker(rank, world, port, out):
                 tgt = r.eval(synth.random_textures(32, 100 + i).to(dev))
             return r, tgt, synth.random_textures(32, 200 + i).to(dev)
         mine, all_losses = sharding.optimise_materials(5, make, 5, 0.01, dev)
-        th.save({"losses": losses, "tex": vs.textures.cpu(), "mine": sorted(mine), "all": all_losses, "p2p_losses": p2p_losses, "p2p_tex": p2p_tex},
+        th.save({"losses": losses, "tex": vs.textures.cpu(), "mine": sorted(mine), "all": all_losses, "p2p_losses": p2p_losses, "p2p_tex": p2p_tex,
+                 "uni_tex": uni_tex, "mc": mc_used},
                 f"{out}/r{rank}.pt")
     finally:
         dist.destroy_process_group()
@@ -85,6 +95,8 @@ def test_two_rank_nccl_view_and_material_sharding(tmp_path):
                                  floor=2e-4, min_fraction=0.998)
     # peer-push mode: replicas bit-identical by construction, same optimisation as the NCCL mode
     assert th.equal(a["p2p_tex"], b["p2p_tex"]) and a["p2p_losses"] == b["p2p_losses"]
+    assert th.equal(a["uni_tex"], a["p2p_tex"]) and th.equal(b["uni_tex"], a["p2p_tex"])     # multicast == unicast all-gather
+    print("NVLS multicast used:", a["mc"], b["mc"])
     np.testing.assert_allclose(np.array(a["p2p_losses"]), g["loss_f64"], rtol=5e-5)
     parity.check_against_arbiter(a["p2p_tex"].numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "2-rank peer-push maps",
                                  floor=2e-4, min_fraction=0.998)
