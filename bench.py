@@ -51,8 +51,8 @@ def parse():
     ap.add_argument("--lights", type=int, default=LIGHTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--view-sharded", action="store_true", help="also time the view-sharded (strong-scaling) mode; default on when N>1")
-    ap.add_argument("--vs-res", type=int, default=2048)
+    ap.add_argument("--no-view-sharded", action="store_true", help="skip the view-sharded (strong-scaling) leg")
+    ap.add_argument("--vs-res", type=int, default=4096)
     ap.add_argument("--vs-lights", type=int, default=256)
     return ap.parse_args()
 
@@ -372,7 +372,9 @@ def run_b200_arm(args):
 
     # ---- view-sharded mode: ONE material, lights split over the ranks, NCCL all-reduce of the gradient ----
     view = None
-    if args.view_sharded or world > 1:
+    if not args.no_view_sharded:
+        del mats
+        th.cuda.empty_cache()
         view = view_sharded_bench(args, dev, world, rank, barrier)
 
     # ---- cpu baseline (rank 0 only, N=1 only) ----

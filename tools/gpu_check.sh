@@ -30,11 +30,11 @@ tail -5 $OUT/bench.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu launch list"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_$TAG.csv \
-      python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_launch_bench.log 2>&1
+      python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-view-sharded > $OUT/ncu_launch_bench.log 2>&1
   grep -c _kernel $OUT/launches_$TAG.csv
   echo "== ncu full capture of the fused kernel"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tile_kernel|texel_kernel<3' -s 8 -c 2 -f -o $OUT/prof_l2adam_$TAG \
-      python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/ncu_full_bench.log 2>&1
+      python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-view-sharded > $OUT/ncu_full_bench.log 2>&1
   ls -la $OUT/*.ncu-rep
 fi
 echo "== done"
