@@ -202,11 +202,6 @@ class PeerShardedOptim:
         per = -(-self.texels // self.world)
         self.chunk = -(-per // self.TILE) * self.TILE
         name = self.group.group_name
-        if hasattr(symm, "enable_symm_mem_for_group"):
-            try:
-                symm.enable_symm_mem_for_group(name)
-            except Exception:
-                pass
         self.tex_sym = symm.empty(9 * self.texels, dtype=th.float32, device=self.device)
         self.recv_sym = symm.empty(self.world * 9 * self.chunk, dtype=th.float32, device=self.device)
         self.h_tex = symm.rendezvous(self.tex_sym, name)
