@@ -83,6 +83,12 @@ constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
 #define SV_STASH 1
 #endif
 constexpr int kStashFloats = 29;
+// SV_PAIR_CHANNELS: inside one texel, independent channels (RGB radiance chain, the 7 gamma-encoded texture channels,
+// the 9 Adam updates) are processed two at a time with the packed FP32x2 instructions — no extra registers, fewer
+// issue slots for the same FMA-pipe work (the scalar kernel is issue-bound).
+#ifndef SV_PAIR_CHANNELS
+#define SV_PAIR_CHANNELS 1
+#endif
 // Development switch: SV_STREAM_ONLY=1 builds a kernel that moves exactly the same bytes through the same TMA ring
 // and stores but skips the shading math — the streaming ceiling of the pipeline design (profiles/r01_variants.txt).
 #ifndef SV_STREAM_ONLY
@@ -692,15 +698,31 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         float* __restrict__ pt = P.tex + p;
         float* __restrict__ pm = P.m + p;
         float* __restrict__ pv = P.v + p;
+#if SV_STREAM_ONLY
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { raw[k] += gt[k]; mk[k] += 1.f; vk[k] += 1.f; }
+#elif SV_PAIR_CHANNELS
+        {
+          // channels are updated two at a time with the packed FP32x2 instructions (same arithmetic, half the FMA-pipe
+          // issue slots); MUFU sqrt/rcp stay per component
+          AdamStep<V2> a2;
+          a2.one_minus_b1 = V2(adam_e.one_minus_b1); a2.b2 = V2(adam_e.b2); a2.one_minus_b2 = V2(adam_e.one_minus_b2);
+          a2.step_size = V2(adam_e.step_size); a2.inv_sqrt_bc2 = V2(adam_e.inv_sqrt_bc2); a2.eps = V2(adam_e.eps);
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            V2 pp(raw[k], raw[k + 1]), mm(mk[k], mk[k + 1]), vv(vk[k], vk[k + 1]);
+            adam_update(pp, mm, vv, V2(gt[k], gt[k + 1]), a2);
+            raw[k] = pp.x; raw[k + 1] = pp.y; mk[k] = mm.x; mk[k + 1] = mm.y; vk[k] = vv.x; vk[k + 1] = vv.y;
+          }
+          adam_update(raw[8], mk[8], vk[8], gt[8], adam_e);
+        }
+#else
+#pragma unroll
+        for (int k = 0; k < 9; ++k) adam_update(raw[k], mk[k], vk[k], gt[k], adam_e);
+#endif
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-          float pk = raw[k];
-#if SV_STREAM_ONLY
-          pk += gt[k]; mk[k] += 1.f; vk[k] += 1.f;
-#else
-          adam_update(pk, mk[k], vk[k], gt[k], adam_e);
-#endif
-          *pt = pk;
+          *pt = raw[k];
           *pm = mk[k];
           *pv = vk[k];
           pt += P.stride;
@@ -1412,9 +1434,12 @@ int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v
   P.pow_state = pow_state;
   // optim_light couples all texels through light_pow every epoch -> one launch per epoch; otherwise up to
   // kMaxEpochs epochs run inside one persistent launch.
-  const int per_launch = pow_state ? 1 : (env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs) < kMaxEpochs
-                                               ? (env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs) < 1 ? 1 : env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", kMaxEpochs))
-                                               : kMaxEpochs);
+  // Long epochs (>= ~1 ms: launch, ramp-up and tail are already < 1 %) gain nothing from persistence and pay ~2 % for
+  // the progress fences (measured at 4096^2 x 64), so they keep one launch per epoch.
+  const bool long_epoch = double(P.texels) * double(geom->n_lights) >= 2.0e8;
+  int per_launch = env_int("SVBRDF_B200_EPOCHS_PER_LAUNCH", long_epoch ? 1 : kMaxEpochs);
+  if (pow_state || per_launch < 1) per_launch = 1;
+  if (per_launch > kMaxEpochs) per_launch = kMaxEpochs;
   for (int e0 = 0; e0 < epochs; e0 += per_launch) {
     const int n = epochs - e0 < per_launch ? epochs - e0 : per_launch;
     for (int i = 0; i < n; ++i) {
