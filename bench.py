@@ -350,6 +350,26 @@ def run_b200_arm(args):
                "h2d_bytes_per_step": stage.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
                "what": "every step re-uploads its [N,3,R,R] fp32 targets from pinned host memory, runs the fused step, reads the loss back"}
 
+        # the same per-step protocol with the targets kept as what they are on disk — uint8 PNG bytes (imageio.py:18-19);
+        # the fused kernel divides by 255 itself (bit-identical to the host division), a quarter of the upload
+        host_u8 = [(t * 255).to(th.uint8).pin_memory() for t in host_targets]
+        stage_u8 = th.empty(stage.shape, dtype=th.uint8, device=dev)
+
+        def e2e_step_u8(i):
+            stage_u8.copy_(host_u8[i % 2], non_blocking=True)
+            a = nv.Adam(LR, 0.9, 0.999, 1e-8, i + 1)
+            nv.check(L.svbrdf_l2_adam_step(ctypes.byref(geom), nv.ptr(o.textures.data), nv.ptr(em), nv.ptr(ev), nv.ptr(stage_u8), 1,
+                                           ctypes.byref(a), nv.ptr(loss_dev), None, nv.ptr(ws), stream), "l2_adam_step")
+            host_loss.copy_(loss_dev, non_blocking=True)
+            th.cuda.current_stream().synchronize()
+
+        for i in range(2):
+            e2e_step_u8(i)
+        ms_u8 = timed(e2e_step_u8, e2e_steps)
+        e2e["uint8_targets"] = {"value": samples_per_step * world * e2e_steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": stage_u8.numel(),
+                                "d2h_bytes_per_step": 4, "ms_per_step": ms_u8 / e2e_steps,
+                                "what": "same protocol, targets uploaded as uint8 (the PNG bytes), decoded in-kernel"}
+
         # the call a user makes: SvbrdfOptim.optim(20 epochs) on host-resident inputs, result back on the host
         host_tex0 = mats[0]["tex0"].cpu().pin_memory()
         host_out = th.empty_like(host_tex0).pin_memory()
