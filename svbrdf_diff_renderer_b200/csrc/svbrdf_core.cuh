@@ -65,6 +65,7 @@ struct Fm<float> {
   static SV_D float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static SV_D float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static SV_D float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static SV_D float mul(float a, float b) { return __fmul_rn(a, b); }     // a rounded product the compiler may not contract into an FMA
   static SV_D float max(float a, float b) { return fmaxf(a, b); }
   static SV_D float min(float a, float b) { return fminf(a, b); }
 #else
@@ -93,6 +94,7 @@ struct Fm<float> {
   static SV_HD float lg2(float x) { return jitter(std::log2(x), true, 8); }
   static SV_HD float ex2(float x) { return jitter(std::exp2(x), false, 16); }
   static SV_HD float fma(float a, float b, float c) { return std::fma(a, b, c); }
+  static SV_HD float mul(float a, float b) { return a * b; }
   static SV_HD float max(float a, float b) { return a > b ? a : b; }
   static SV_HD float min(float a, float b) { return a < b ? a : b; }
 #endif
@@ -114,6 +116,7 @@ struct Fm<double> {
   static SV_HD double lg2(double x) { return ::log2(x); }
   static SV_HD double ex2(double x) { return ::exp2(x); }
   static SV_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
+  static SV_HD double mul(double a, double b) { return a * b; }
   static SV_HD double max(double a, double b) { return a > b ? a : b; }
   static SV_HD double min(double a, double b) { return a < b ? a : b; }
 };
@@ -169,6 +172,7 @@ struct Fm<V2> {
   static SV_HD V2 ex2(const V2& a) { return V2(S::ex2(a.x), S::ex2(a.y)); }
   static SV_HD V2 max(const V2& a, const V2& b) { return V2(S::max(a.x, b.x), S::max(a.y, b.y)); }
   static SV_HD V2 min(const V2& a, const V2& b) { return V2(S::min(a.x, b.x), S::min(a.y, b.y)); }
+  static SV_HD V2 mul(const V2& a, const V2& b) { return a * b; }            // __fmul2_rn: never contracted
 #if defined(__CUDA_ARCH__)
   static SV_D V2 fma(const V2& a, const V2& b, const V2& c) { return f2v(__ffma2_rn(v2f(a), v2f(b), v2f(c))); }
 #else
@@ -240,7 +244,11 @@ struct Grads {       // accumulated over lights (without the constant image-grad
   T n[3];
   T pw[3];           // sum of gfp_c * fp_c = pw_c * dL/dpw_c (only when requested)
   T loss;            // sum of squared differences (L2 modes)
+  T loss_g;          // second lane of the packed loss accumulator (SV_PAIR_RG); grads_loss() returns the total
 };
+
+template <typename T>
+SV_HD T grads_loss(const Grads<T>& g) { return g.loss + g.loss_g; }
 
 // Texel centre: ((j + 0.5)/res - 0.5) * size in the reference's fp32 op order
 // (microfacet.py:16-19; y is negated, rows index y).
@@ -308,7 +316,7 @@ SV_HD void texel_prologue(const T t[9], const T pw[3], Texel<T>& tx, TexelAux<T>
 template <typename T>
 SV_HD void grads_zero(Grads<T>& g) {
   for (int c = 0; c < 3; ++c) g.kdp[c] = g.sF[c] = g.n[c] = g.pw[c] = T(0);
-  g.a2 = g.k = g.loss = T(0);
+  g.a2 = g.k = g.loss = g.loss_g = T(0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,6 +353,14 @@ struct LightGeom {   // per light, texture independent
 #define SV_PAIR_RG 1
 #endif
 
+// SV_OUT_FROM_SLOPE: in the gradient modes the gamma slope Icl^(1/g - 1) is needed anyway, so the encoded value
+// Icl^(1/g) is formed as slope * Icl — one multiplication instead of a second MUFU.EX2 per channel: 13 -> 10 MUFU per
+// pixel.light on the co-located path.  The extra rounding (one multiplication, and an ex2 argument 1.2x larger) is
+// below the lg2/ex2 approximation error; the forward render (kRender) uses the same expression.
+#ifndef SV_OUT_FROM_SLOPE
+#define SV_OUT_FROM_SLOPE 1
+#endif
+
 #if SV_PAIR_RG && defined(__CUDA_ARCH__)
 template <int MODE, bool WANT_POW>
 SV_D void channels_rg(const float kdp[3], const float Fp[3], float w, float Q, const float io[3], float out[3], Grads<float>& g,
@@ -361,18 +377,26 @@ SV_D void channels_rg(const float kdp[3], const float Fp[3], float w, float Q, c
   const float IclB = S::min(S::max(IB, float(kEps)), 1.f);
   const V2 lgRG(S::lg2(IclRG.x), S::lg2(IclRG.y));
   const float lgB = S::lg2(IclB);
-  const V2 eo = lgRG * V2(1.0 / kGamma), es = lgRG * V2(1.0 / kGamma - 1.0);
+  const V2 es = lgRG * V2(1.0 / kGamma - 1.0);
   const V2 slopeRG(S::ex2(es.x), S::ex2(es.y));
   const float slopeB = S::ex2(lgB * float(1.0 / kGamma - 1.0));
   V2 upRG;
   float upB;
   if (MODE == kL2) {
+#if SV_OUT_FROM_SLOPE
+    const V2 oRG = slopeRG * IclRG;                            // Icl^(1/g) = Icl^(1/g - 1) * Icl
+    const float oB = S::mul(slopeB, IclB);                     // rounded like the render's (no FMA contraction with the subtraction)
+#else
+    const V2 eo = lgRG * V2(1.0 / kGamma);
     const V2 oRG(S::ex2(eo.x), S::ex2(eo.y));
     const float oB = S::ex2(lgB * float(1.0 / kGamma));
+#endif
     upRG = oRG - V2(io[0], io[1]);
     upB = oB - io[2];
-    const V2 sq = upRG * upRG;
-    g.loss = S::fma(upB, upB, g.loss + (sq.x + sq.y));
+    // R^2 and G^2 accumulate as a packed pair (loss, loss_g), B^2 joins the first lane: 2 issue slots instead of 4
+    const V2 l2 = F::fma(upRG, upRG, V2(g.loss, g.loss_g));
+    g.loss_g = l2.y;
+    g.loss = S::fma(upB, upB, l2.x);
   } else {
     upRG = V2(io[0], io[1]);
     upB = io[2];
@@ -382,7 +406,10 @@ SV_D void channels_rg(const float kdp[3], const float Fp[3], float w, float Q, c
   const float gIB = (IB == IclB) ? upB * slopeB : 0.f;
   const V2 gfpRG = gIRG * ww;
   const float gfpB = gIB * w;
-  g.kdp[0] += gfpRG.x; g.kdp[1] += gfpRG.y; g.kdp[2] += gfpB;
+  {
+    const V2 k2 = V2(g.kdp[0], g.kdp[1]) + gfpRG;
+    g.kdp[0] = k2.x; g.kdp[1] = k2.y; g.kdp[2] += gfpB;
+  }
   const V2 a = gIRG * fpRG, b = gfpRG * FpRG;
   gw = S::fma(gIB, fpB, a.x + a.y);
   gQ = S::fma(gfpB, Fp[2], b.x + b.y);
@@ -406,7 +433,13 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
     Icl[c] = F::min(F::max(I[c], T(kEps)), T(1));             // microfacet.py:120
   }
   if (MODE == kRender) {
+#if SV_OUT_FROM_SLOPE
+    // same expression as the gradient modes below, so a rendered target is reproduced bit for bit by the L2 forward
+    // (the ground truth is then an exact fixed point of the optimisation, as it is for the reference)
+    for (int c = 0; c < 3; ++c) out[c] = F::mul(F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma - 1.0)), Icl[c]);
+#else
     for (int c = 0; c < 3; ++c) out[c] = F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma));
+#endif
     return;
   }
   // d out/d I = (1/gamma) Icl^(1/gamma - 1) = (1/gamma) out/Icl, zero outside the clamp (inclusive edges);
@@ -426,8 +459,12 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
 #else
   for (int c = 0; c < 3; ++c) {
     const T lg = F::lg2(Icl[c]);
-    if (MODE == kL2) o[c] = F::ex2(lg * T(1.0 / kGamma));
     slope[c] = F::ex2(lg * T(1.0 / kGamma - 1.0));
+#if SV_OUT_FROM_SLOPE
+    if (MODE == kL2) o[c] = F::mul(slope[c], Icl[c]);         // Icl^(1/g) = Icl^(1/g - 1) * Icl: a multiplication instead of a MUFU
+#else
+    if (MODE == kL2) o[c] = F::ex2(lg * T(1.0 / kGamma));
+#endif
   }
 #endif
   for (int c = 0; c < 3; ++c) {

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
   // block partials: loss and light-power gradient (fixed order => deterministic)
   constexpr bool kHasLoss = (MODE == kModeL2Grad || MODE == kModeL2Adam);
   if (kHasLoss || WANT_POW) {
-    float r[4] = {valid ? g.loss : 0.f, valid ? g.pw[0] : 0.f, valid ? g.pw[1] : 0.f, valid ? g.pw[2] : 0.f};
+    float r[4] = {valid ? grads_loss(g) : 0.f, valid ? g.pw[0] : 0.f, valid ? g.pw[1] : 0.f, valid ? g.pw[2] : 0.f};
     warp_reduce4(r);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
@@ -519,6 +519,30 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                : "memory");
 }
 
+
+// The producer role is executed by a WHOLE warp in uniform control flow; only the instructions with side effects
+// (bulk copies, mbarrier arrivals, bulk-group commits/waits) are predicated on one elected lane.  With a single thread
+// running the role (`if (tid == X)`), ptxas cannot prove that the operands of the uniform-datapath UBLKCP instruction
+// are warp-uniform and wraps every copy in a ~14-instruction lane-serialisation loop (PLOP3 / R2UR / BRA.U.ANY): the
+// producer thread then executes ~15 dependent instructions per plane segment — 54-81 segments per tile — and becomes
+// the bottleneck of the pipeline (ncu source view, profiles/r01_s2_ts_producer_bound.txt).
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Warp-uniform wait: every lane polls, the vote makes the loop exit provably uniform for the compiler.
+__device__ __forceinline__ void mbar_wait_uniform(unsigned long long* bar, unsigned parity) {
+  while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+  }
+}
 
 // Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
 template <int MODE>
@@ -749,7 +773,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       }
     }
     if (valid) {
-      loss_acc[0] += g.loss;
+      loss_acc[0] += grads_loss(g);
 #pragma unroll
       for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c];
     }
@@ -990,7 +1014,7 @@ __device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __
       }
     }
     if (valid) {
-      loss_acc[0] += g.loss.x + g.loss.y;
+      loss_acc[0] += g.loss.x + g.loss.y + g.loss_g.x + g.loss_g.y;
 #pragma unroll
       for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c].x + g.pw[c].y;
     }
@@ -1008,6 +1032,7 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   unsigned slot = 0, phase = 0;
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  const bool leader = elect_one();                       // the whole warp runs this role; one lane issues
 
   const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   for (int e = 0; e < P.epochs; ++e) {
@@ -1018,25 +1043,26 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
       const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
       const unsigned need = (unsigned(e - 1) * my_tiles + local + publish_every) / publish_every * publish_every;
       for (int w = 0; w < SH::kCW; ++w)
-        while (s_done[w] < need) {
+        while (!__any_sync(0xffffffffu, s_done[w] >= need)) {
         }
     }
     const long long p0 = rotate_tile(tile, P.tile_rotate, n_tiles) * SH::kTile;
     const unsigned len = unsigned(min((long long)SH::kTile, P.texels - p0));      // texels in this tile (multiple of 4)
     auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
       // `planes` plane segments of `len` elements each, starting at element p0 of consecutive planes of `base`
-      mbar_wait(&empty[slot], phase ^ 1);
+      mbar_wait_uniform(&empty[slot], phase ^ 1);
       unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
       const unsigned bar = smem_u32(&full[slot]);
       const unsigned seg = len * elem_bytes;
-      mbar_expect_tx(&full[slot], seg * planes);
+      if (leader) mbar_expect_tx(&full[slot], seg * planes);
       const unsigned char* src = static_cast<const unsigned char*>(base) + size_t(p0) * elem_bytes;
       const size_t src_step = size_t(P.stride) * elem_bytes;
       const unsigned dst_step = unsigned(SH::kTile) * elem_bytes;
       for (int j = 0; j < planes; ++j) {
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                     "r"(seg), "r"(bar)
-                     : "memory");
+        if (leader)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                       "r"(seg), "r"(bar)
+                       : "memory");
         dst += dst_step;
         src += src_step;
       }
@@ -1055,6 +1081,429 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
       fill(P.v, 4, 9);
     }
   }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_kernel_ts: the same pipeline with the results leaving through TMA as well ("store-back").
+//
+// In tile_kernel every consumer thread ends a tile with up to 27 STG, each with its own 64-bit pointer increment
+// (IADD3 + IADD3.X) — 81 issue slots per texel in an issue-bound kernel — and multi-epoch launches need generic->async
+// proxy fences so the next epoch's TMA loads see those stores.  Here
+//   * the tile's 9 texture planes live in a dedicated double-buffered shared-memory segment T[2] for the whole tile
+//     (TMA-loaded, read by the prologue, re-read by the epilogue instead of a register/stash copy),
+//   * the consumers overwrite T in place with the new parameters (fused mode) or the gradient (L2-grad / VJP), and the
+//     Adam moments in place in the ring slots they arrived in: 27 STS with immediate offsets,
+//   * one fence.proxy.async per thread + one mbarrier arrival per warp hands the tile to the producer thread, which
+//     writes it out with 9-27 bulk copies (cp.async.bulk.global.shared::cta, SASS UBLKCP) and recycles the slots once
+//     the copies have read shared memory.
+// Loads and stores of one tile are now issued by the same thread in the same (async) proxy: the cross-epoch hazard is
+// covered by cp.async.bulk.wait_group before a tile is loaded again.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStashTs = 19;            // the raw texel stays in T: only the 19 derived values are parked
+
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_ns(unsigned long long* bar, unsigned parity, unsigned ns) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_n(unsigned long long* bar, unsigned n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
+// 1-D TMA bulk copy shared -> global (bytes % 16 == 0, both addresses 16-byte aligned), tracked by bulk async-groups.
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, unsigned src_smem, unsigned bytes) {
+#if !defined(SV_TS_NOSTORE)
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+#endif
+}
+
+struct TsBars {
+  unsigned long long* full;     // [slots] ring slot loaded (TMA complete_tx)
+  unsigned long long* empty;    // [slots] ring slot free (CW consumer-warp arrivals, or CW arrivals by the producer after a store-back)
+  unsigned long long* t_full;   // [2] texture segment loaded
+  unsigned long long* t_empty;  // [2] texture segment stored and free
+  unsigned long long* t_done;   // [2] all consumer warps have written the tile's results (CW arrivals)
+};
+
+template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
+__device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring, float* T,
+                                                  const TsBars B, float* stash, float (*s_red)[SH::kCW][4]) {
+  typedef typename IoLoad<TGT>::elem elem;
+  constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int N = P.n_lights, S = P.slots;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
+  float pw[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
+
+  unsigned slot = 0, phase = 0;
+  auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&B.empty[s]); };
+
+  unsigned t = 0;                                       // tiles of this CTA so far, over all epochs
+  for (int e = 0; e < P.epochs; ++e) {
+  AdamStep<float> adam_e = P.adam;
+  adam_e.step_size = P.step_size[e];
+  adam_e.inv_sqrt_bc2 = P.inv_sqrt_bc2[e];
+  float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    const long long p = tile * SH::kTile + tid;
+    const bool valid = p < P.texels;
+    const unsigned b = t & 1u;
+    float* Tb = T + size_t(b) * 9 * SH::kTile + tid;    // this thread's column of the tile's texture segment
+
+    // ---- texel prologue ----
+    float raw[9], tt[9];
+    bool outer[9];
+    mbar_wait(&B.t_full[b], (t >> 1) & 1u);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) raw[k] = valid ? Tb[k * SH::kTile] : 0.f;
+    clamp_outer<MODE>(raw, tt, outer);
+    Texel<float> tx;
+    TexelAux<float> ax;
+    {
+      const long long pc = valid ? p : 0;
+      int row, col;
+      if (P.texels < (1ll << 32)) {
+        row = int(__umul64hi((unsigned long long)pc, P.res_magic));        // exact floor(pc/res) for pc < 2^32
+        col = int(unsigned(pc) - unsigned(row) * unsigned(P.res));
+      } else {
+        row = int(pc / P.res);
+        col = int(pc - (long long)row * P.res);
+      }
+      texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+    }
+#if SV_STREAM_ONLY
+    tx.px = tt[0]; ax.mx = tt[1];
+#else
+    texel_prologue(tt, pw, tx, ax);
+    {
+      float* st = stash + tid;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) st[k * SH::kTile] = ax.dpow[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { st[(7 + k) * SH::kTile] = ax.d[k]; st[(10 + k) * SH::kTile] = ax.oms[k]; }
+      st[13 * SH::kTile] = ax.rough; st[14 * SH::kTile] = ax.alpha;
+      st[15 * SH::kTile] = ax.mx; st[16 * SH::kTile] = ax.my; st[17 * SH::kTile] = ax.mz; st[18 * SH::kTile] = ax.rlen;
+    }
+#endif
+    Grads<float> g;
+    grads_zero(g);
+
+    // ---- lights, 3 per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+      float in[kChunkLights][3];
+      mbar_wait(&B.full[slot], phase);
+      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
+      if (i0 + kChunkLights <= N) {
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]);
+        }
+        release(slot);
+        advance();
+#if SV_STREAM_ONLY
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
+#else
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+          float o3[3];
+          shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+        }
+#endif
+      } else {
+#pragma unroll
+        for (int j = 0; j < kChunkLights; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
+        }
+        release(slot);
+        advance();
+#pragma unroll
+        for (int j = 0; j < kChunkLights - 1; ++j) {       // a partial chunk holds at most kChunkLights-1 lights
+          if (i0 + j < N) {
+            float o3[3];
+            shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+          }
+        }
+      }
+    }
+
+    // ---- epilogue ----
+    float gt[9];
+#if SV_STREAM_ONLY
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gt[k] = g.loss + tx.px;
+#else
+    {
+      const volatile float* st = stash + tid;
+      const volatile float* tv = Tb;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) raw[k] = valid ? tv[k * SH::kTile] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ax.dpow[k] = st[k * SH::kTile];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { ax.d[k] = st[(7 + k) * SH::kTile]; ax.oms[k] = st[(10 + k) * SH::kTile]; }
+      ax.rough = st[13 * SH::kTile]; ax.alpha = st[14 * SH::kTile];
+      ax.mx = st[15 * SH::kTile]; ax.my = st[16 * SH::kTile]; ax.mz = st[17 * SH::kTile]; ax.rlen = st[18 * SH::kTile];
+      clamp_outer<MODE>(raw, tt, outer);
+      ax.in3 = (tt[3] >= -1.f) && (tt[3] <= 1.f);
+      ax.in4 = (tt[4] >= -1.f) && (tt[4] <= 1.f);
+      ax.planar_free = (ax.mx * ax.mx + ax.my * ax.my) <= (1.f - float(kEps));
+    }
+    texel_epilogue<float, COLOC>(tx, ax, pw, g, P.scale, outer, gt);
+#endif
+    if (MODE == kModeL2Adam) {
+      float mk[9], vk[9];
+      mbar_wait(&B.full[slot], phase);
+      float* sm = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + tid;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) mk[k] = sm[k * SH::kTile];
+      advance();                                           // not released: the slot is written back in place below
+      mbar_wait(&B.full[slot], phase);
+      float* sv = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + tid;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) vk[k] = sv[k * SH::kTile];
+      advance();
+#if SV_STREAM_ONLY
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { raw[k] += gt[k]; mk[k] += 1.f; vk[k] += 1.f; }
+#elif SV_PAIR_CHANNELS
+      {
+        AdamStep<V2> a2;
+        a2.one_minus_b1 = V2(adam_e.one_minus_b1); a2.b2 = V2(adam_e.b2); a2.one_minus_b2 = V2(adam_e.one_minus_b2);
+        a2.step_size = V2(adam_e.step_size); a2.inv_sqrt_bc2 = V2(adam_e.inv_sqrt_bc2); a2.eps = V2(adam_e.eps);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          V2 pp(raw[k], raw[k + 1]), mm(mk[k], mk[k + 1]), vv(vk[k], vk[k + 1]);
+          adam_update(pp, mm, vv, V2(gt[k], gt[k + 1]), a2);
+          raw[k] = pp.x; raw[k + 1] = pp.y; mk[k] = mm.x; mk[k + 1] = mm.y; vk[k] = vv.x; vk[k + 1] = vv.y;
+        }
+        adam_update(raw[8], mk[8], vk[8], gt[8], adam_e);
+      }
+#else
+#pragma unroll
+      for (int k = 0; k < 9; ++k) adam_update(raw[k], mk[k], vk[k], gt[k], adam_e);
+#endif
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        Tb[k * SH::kTile] = raw[k];
+        sm[k * SH::kTile] = mk[k];
+        sv[k * SH::kTile] = vk[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Tb[k * SH::kTile] = gt[k];
+    }
+    // hand the tile to the producer: generic-proxy writes -> visible to the async proxy, then one arrival per warp
+#if !defined(SV_TS_NOFENCE)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&B.t_done[b]);
+    if (valid) {
+      loss_acc[0] += grads_loss(g);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) loss_acc[1 + c] += g.pw[c];
+    }
+  }
+  epoch_end<SH::kCW>(P, e, loss_acc, s_red, tid >> 5, lane);
+  }
+}
+
+template <int MODE, int TGT, typename SH>
+__device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char* ring, float* T, const TsBars B) {
+  typedef typename IoLoad<TGT>::elem elem;
+  const int N = P.n_lights, S = P.slots;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
+  const unsigned CL = unsigned((N + kChunkLights - 1) / kChunkLights);        // light chunks per tile
+  const unsigned C = CL + (MODE == kModeL2Adam ? 2u : 0u);                     // ring chunks per tile
+  const unsigned M = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const unsigned total = M * unsigned(P.epochs);
+  float* const out_base = (MODE == kModeL2Adam) ? P.tex : P.out;
+  unsigned slot = 0, phase = 0;
+  auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  const bool leader = elect_one();                       // the whole warp runs this role; one lane issues (and owns the bulk groups)
+
+  unsigned stored = 0;                                    // tiles written back so far
+  // Write tile `stored` back if all consumer warps are done with it (non-blocking otherwise).
+  auto service = [&]() -> bool {
+    if (stored >= total) return false;
+    const unsigned b = stored & 1u;
+    if (!__any_sync(0xffffffffu, mbar_test_wait(&B.t_done[b], (stored >> 1) & 1u))) return false;
+    const long long tile = (long long)blockIdx.x + (long long)(stored % M) * gridDim.x;
+    const long long p0 = tile * SH::kTile;
+    const unsigned seg = unsigned(min((long long)SH::kTile, P.texels - p0)) * 4u;
+    unsigned src = smem_u32(T) + b * unsigned(SH::kSlotBytes);
+    float* dst = out_base + p0;
+#pragma unroll 1
+    for (int k = 0; k < 9; ++k) {
+      if (leader) tma_store_1d(dst, src, seg);
+      src += SH::kTile * 4;
+      dst += P.stride;
+    }
+    unsigned sm = 0, sv = 0;
+    if (MODE == kModeL2Adam) {
+      sm = (stored * C + CL) % unsigned(S);
+      sv = sm + 1 == unsigned(S) ? 0u : sm + 1;
+      unsigned srcm = smem_u32(ring) + sm * unsigned(SH::kSlotBytes), srcv = smem_u32(ring) + sv * unsigned(SH::kSlotBytes);
+      float* dm = P.m + p0;
+      float* dv = P.v + p0;
+#pragma unroll 1
+      for (int k = 0; k < 9; ++k) {
+        if (leader) {
+          tma_store_1d(dm, srcm, seg);
+          tma_store_1d(dv, srcv, seg);
+        }
+        srcm += SH::kTile * 4; srcv += SH::kTile * 4;
+        dm += P.stride; dv += P.stride;
+      }
+    }
+    if (leader) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory has been read: the segments may be reused
+      mbar_arrive(&B.t_empty[b]);
+      if (MODE == kModeL2Adam) {
+        mbar_arrive_n(&B.empty[sm], SH::kCW);
+        mbar_arrive_n(&B.empty[sv], SH::kCW);
+      }
+    }
+    __syncwarp();
+    ++stored;
+    return true;
+  };
+  auto wait_serving = [&](unsigned long long* bar, unsigned parity) {
+    while (!__any_sync(0xffffffffu, mbar_try_wait_ns(bar, parity, 400u))) service();
+  };
+
+  unsigned t = 0;
+  for (int e = 0; e < P.epochs; ++e) {
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    const long long p0 = tile * SH::kTile;
+    const unsigned len = unsigned(min((long long)SH::kTile, P.texels - p0));      // texels in this tile (multiple of 4)
+    const unsigned b = t & 1u;
+    wait_serving(&B.t_empty[b], ((t >> 1) & 1u) ^ 1u);
+    if (e > 0 && leader) {
+      // this tile was written back M >= 4 store groups ago; all but the most recent group are complete after this wait
+      asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    }
+    {
+      unsigned dst = smem_u32(T) + b * unsigned(SH::kSlotBytes);
+      const unsigned bar = smem_u32(&B.t_full[b]);
+      const unsigned seg = len * 4u;
+      if (leader) mbar_expect_tx(&B.t_full[b], seg * 9u);
+      const float* src = P.tex + p0;
+      for (int j = 0; j < 9; ++j) {
+        if (leader)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                       "r"(seg), "r"(bar)
+                       : "memory");
+        dst += SH::kTile * 4;
+        src += P.stride;
+      }
+    }
+    auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
+      wait_serving(&B.empty[slot], phase ^ 1);
+      unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
+      const unsigned bar = smem_u32(&B.full[slot]);
+      const unsigned seg = len * elem_bytes;
+      if (leader) mbar_expect_tx(&B.full[slot], seg * planes);
+      const unsigned char* src = static_cast<const unsigned char*>(base) + size_t(p0) * elem_bytes;
+      const size_t src_step = size_t(P.stride) * elem_bytes;
+      const unsigned dst_step = unsigned(SH::kTile) * elem_bytes;
+      for (int j = 0; j < planes; ++j) {
+        if (leader)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                       "r"(seg), "r"(bar)
+                       : "memory");
+        dst += dst_step;
+        src += src_step;
+      }
+      advance();
+    };
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+      const int nl = min(kChunkLights, N - i0);
+      fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
+      service();
+    }
+    if (MODE == kModeL2Adam) {
+      fill(P.m, 4, 9);
+      fill(P.v, 4, 9);
+    }
+  }
+  }
+  // drain: the last tiles are written back as their consumers finish
+  while (stored < total) {
+    const unsigned b = stored & 1u;
+    while (!__any_sync(0xffffffffu, mbar_try_wait_ns(&B.t_done[b], (stored >> 1) & 1u, 2000u))) {
+    }
+    service();
+  }
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int MODE, bool WANT_POW, int TGT, typename SH>
+__global__ void __maxnreg__(SH::kMaxReg) tile_kernel_ts(const Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: ring [slots] | T [2] | barriers | light geometry 2*N float4 | stash [19 planes]
+  unsigned char* ring = smem;
+  float* T = reinterpret_cast<float*>(smem + size_t(P.slots) * SH::kSlotBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots + 2) * SH::kSlotBytes);
+  TsBars B;
+  B.full = bars;
+  B.empty = B.full + P.slots;
+  B.t_full = B.empty + P.slots;
+  B.t_empty = B.t_full + 2;
+  B.t_done = B.t_empty + 2;
+  float4* s_geo = reinterpret_cast<float4*>(B.t_done + 2);
+  float* stash = reinterpret_cast<float*>(s_geo + 2 * P.n_lights);
+  __shared__ float s_red[2][SH::kCW][4];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < P.slots; ++s) {
+      mbar_init(&B.full[s], 1);
+      mbar_init(&B.empty[s], SH::kCW);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&B.t_full[b], 1);
+      mbar_init(&B.t_empty[b], 1);
+      mbar_init(&B.t_done[b], SH::kCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
+
+  if (tid >= SH::kConsumers) {
+    tile_producer_ts<MODE, TGT, SH>(P, ring, T, B);               // whole warp, uniform control flow
+  } else {
+    if (coloc) tile_consumer_ts<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, T, B, stash, s_red);
+    else tile_consumer_ts<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, T, B, stash, s_red);
   }
 }
 
@@ -1083,7 +1532,7 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
   const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
 
   if (tid >= SH::kConsumers) {
-    if (tid == SH::kConsumers) tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);
+    tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);    // whole warp, uniform control flow
   } else {
     if (SH::kLanes == 2) {
       if (coloc) tile_consumer2<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
@@ -1336,9 +1785,57 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   return int(cudaGetLastError());
 }
 
+// tile_kernel_ts (results written back by TMA): scalar shape, local outputs only (the peer-push mode keeps per-thread
+// stores to the owner's memory).
+template <int MODE, bool WANT_POW, int TGT, typename SH>
+static int launch_tile_ts(Params P, cudaStream_t st) {
+  const bool trace = env_int("SVBRDF_B200_TRACE", 0) != 0;
+  Device d;
+  if (int e = device_info(&d)) return e;
+  const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
+  const size_t stash_bytes = size_t(kStashTs) * SH::kTile * 4;
+  const size_t static_smem = 1024;                                     // s_red (static __shared__) + slack
+  const size_t fixed = 2 * size_t(SH::kSlotBytes) + geo + stash_bytes + (2 * 64 + 6) * 8 + 64;
+  if (size_t(d.smem_optin) < fixed + static_smem + 3 * size_t(SH::kSlotBytes)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
+  int slots = env_int("SVBRDF_B200_SLOTS", 0);
+  if (slots <= 0) slots = int((size_t(d.smem_optin) - static_smem - fixed) / SH::kSlotBytes);
+  const int need = chunks_per_tile<MODE>(P.n_lights) - 1;              // the texture chunk is not in the ring
+  if (slots > 2 * need) slots = 2 * need;
+  if (slots > 64) slots = 64;
+  if (slots < 3) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
+  P.slots = slots;
+  const size_t smem = size_t(slots + 2) * SH::kSlotBytes + size_t(2 * slots + 6) * 8 + geo + stash_bytes + 16;
+  if (smem + static_smem > size_t(d.smem_optin)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
+  auto kern = tile_kernel_ts<MODE, WANT_POW, TGT, SH>;
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
+  long long grid = d.sms;
+  if (grid > n_tiles) grid = n_tiles;
+  P.counters = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
+  if (grid > kRowsPerEpoch) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (P.epochs > 1 && n_tiles / grid < 4) {          // a tile must be >= 3 store groups old before it is loaded again
+    Params Q = P;
+    for (int e = 0; e < P.epochs; ++e) {
+      Q.epochs = 1;
+      Q.step_size[0] = P.step_size[e];
+      Q.inv_sqrt_bc2[0] = P.inv_sqrt_bc2[e];
+      Q.loss_out = P.loss_out ? P.loss_out + e : nullptr;
+      if (int err = launch_tile_ts<MODE, WANT_POW, TGT, SH>(Q, st)) return err;
+    }
+    return 0;
+  }
+  if (trace) fprintf(stderr, "[svbrdf] tile_kernel_ts mode %d tile %d slots %d smem %zu grid %lld\n", MODE, SH::kTile, slots, smem, grid);
+  kern<<<int(grid), SH::kThreads, smem, st>>>(P);
+  return int(cudaGetLastError());
+}
+
 template <int MODE, bool WANT_POW, int TGT>
 static int launch_tile(Params P, cudaStream_t st) {
   if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  const bool out_ok = MODE == kModeL2Adam || (reinterpret_cast<uintptr_t>(P.out) & 15) == 0;
+  if (P.push_world == 0 && P.tile_rotate == 0 && out_ok && !env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT) && env_int("SVBRDF_B200_TSTORE", 1))
+    return launch_tile_ts<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 #if SV_ENABLE_PACKED
   if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
 #endif

@@ -70,7 +70,7 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
       if (mode == 0) continue;
       T gt[9];
       texel_epilogue<T, COLOC>(tx, ax, pw, g, scale, outer, gt);
-      loss_acc += double(g.loss);
+      loss_acc += double(g.loss) + double(g.loss_g);
       for (int ch = 0; ch < 3; ++ch) gp_acc[ch] += double(g.pw[ch]) * double(scale);
       if (mode == 3) {
         AdamStep<T> a;
@@ -142,7 +142,7 @@ void run_v2(int mode, float* tex, const float* cam, const float* light, const fl
     if (mode == 0) continue;
     T gt[9];
     texel_epilogue<T, COLOC>(tx, ax, pw, g, scale, outer, gt);
-    loss_acc += double(g.loss.x) + double(g.loss.y);
+    loss_acc += double(g.loss.x) + double(g.loss.y) + double(g.loss_g.x) + double(g.loss_g.y);
     for (int ch = 0; ch < 3; ++ch) gp_acc[ch] += (double(g.pw[ch].x) + double(g.pw[ch].y)) * double(scale.x);
     if (mode == 3) {
       AdamStep<T> a;

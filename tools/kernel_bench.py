@@ -51,12 +51,28 @@ def main():
         "tma2s8": {"SVBRDF_B200_CTAS_PER_SM": "2", "SVBRDF_B200_SLOTS": "8"},
         "tma2s4": {"SVBRDF_B200_CTAS_PER_SM": "2", "SVBRDF_B200_SLOTS": "4"},
     }
-    keys = ("SVBRDF_B200_FORCE_LDG", "SVBRDF_B200_CTAS_PER_SM", "SVBRDF_B200_SLOTS")
+    keys = ("SVBRDF_B200_FORCE_LDG", "SVBRDF_B200_CTAS_PER_SM", "SVBRDF_B200_SLOTS", "SVBRDF_B200_PACKED", "SVBRDF_B200_TSTORE")
     out = {}
+
+    def preset(name):
+        """`ldg`, or tma<ctas>[s<slots>][p][n] (p = packed FP32x2 shape, n = per-thread STG instead of TMA store-back)."""
+        if name in presets:
+            return presets[name]
+        import re
+        mo = re.fullmatch(r"tma(\d)(?:s(\d+))?(p)?(n)?", name)
+        env = {"SVBRDF_B200_CTAS_PER_SM": mo.group(1)}
+        if mo.group(2):
+            env["SVBRDF_B200_SLOTS"] = mo.group(2)
+        if mo.group(3):
+            env["SVBRDF_B200_PACKED"] = "1"
+        if mo.group(4):
+            env["SVBRDF_B200_TSTORE"] = "0"
+        return env
+
     for name in a.variants.split(";"):
         for k in keys:
             os.environ.pop(k, None)
-        os.environ.update(presets[name])
+        os.environ.update(preset(name))
         state = [(t, x.clone(), th.zeros_like(x), th.zeros_like(x)) for t, x in mats]
 
         def step(i, k=[0]):
