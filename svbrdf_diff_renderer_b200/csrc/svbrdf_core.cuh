@@ -172,7 +172,9 @@ struct Fm<V2> {
   static SV_HD V2 ex2(const V2& a) { return V2(S::ex2(a.x), S::ex2(a.y)); }
   static SV_HD V2 max(const V2& a, const V2& b) { return V2(S::max(a.x, b.x), S::max(a.y, b.y)); }
   static SV_HD V2 min(const V2& a, const V2& b) { return V2(S::min(a.x, b.x), S::min(a.y, b.y)); }
-  static SV_HD V2 mul(const V2& a, const V2& b) { return a * b; }            // __fmul2_rn: never contracted
+  // per component on purpose: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (checked with
+  // cuobjdump), so a packed product is not a "rounded product" once a packed add/sub consumes it
+  static SV_HD V2 mul(const V2& a, const V2& b) { return V2(S::mul(a.x, b.x), S::mul(a.y, b.y)); }
 #if defined(__CUDA_ARCH__)
   static SV_D V2 fma(const V2& a, const V2& b, const V2& c) { return f2v(__ffma2_rn(v2f(a), v2f(b), v2f(c))); }
 #else
@@ -384,7 +386,9 @@ SV_D void channels_rg(const float kdp[3], const float Fp[3], float w, float Q, c
   float upB;
   if (MODE == kL2) {
 #if SV_OUT_FROM_SLOPE
-    const V2 oRG = slopeRG * IclRG;                            // Icl^(1/g) = Icl^(1/g - 1) * Icl
+    // Icl^(1/g) = Icl^(1/g - 1) * Icl.  Two scalar FMULs, not one FMUL2: ptxas would fuse the packed product with the
+    // subtraction below into an FFMA2 and the L2 forward would no longer reproduce the render bit for bit.
+    const V2 oRG(S::mul(slopeRG.x, IclRG.x), S::mul(slopeRG.y, IclRG.y));
     const float oB = S::mul(slopeB, IclB);                     // rounded like the render's (no FMA contraction with the subtraction)
 #else
     const V2 eo = lgRG * V2(1.0 / kGamma);

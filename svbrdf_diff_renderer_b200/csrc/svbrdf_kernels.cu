@@ -26,6 +26,7 @@
 // Per-light geometry (2 x float4 per light) is staged in shared memory once per CTA.  Whether
 // every light is co-located with its camera is detected while staging; co-located captures
 // (everything the reference's capture code emits, capture.py:70-71) take the folded loop body.
+#include <cuda.h>              // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -98,6 +99,12 @@ constexpr int kStashFloats = 29;
 enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3 };
 
 struct Params {
+  // tile_kernel_ts: 2-D TMA descriptors {texel, plane} of the planar arrays (box = 160 texels x 9 planes)
+  alignas(64) CUtensorMap tm_tex;   // textures [9 planes]; also the store target of the fused mode
+  alignas(64) CUtensorMap tm_io;    // targets / grad_out [3N planes], f32 or u8
+  alignas(64) CUtensorMap tm_m;     // Adam moments [9 planes]
+  alignas(64) CUtensorMap tm_v;
+  alignas(64) CUtensorMap tm_out;   // gradient output [9 planes] (L2-grad / VJP)
   float* tex;            // [9] planes (read-only except kModeL2Adam)
   float* m;              // Adam first moment  (kModeL2Adam)
   float* v;              // Adam second moment (kModeL2Adam)
@@ -1101,6 +1108,33 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
 // covered by cp.async.bulk.wait_group before a tile is loaded again.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStashTs = 19;            // the raw texel stays in T: only the 19 derived values are parked
+// 2-D TMA boxes: a tile (480 texels x 9 planes) moves as 3 boxes of 160 texels x 9 planes — 3 instructions per ring slot
+// instead of 9 one-plane bulk copies, 27 per tile instead of 81 with the store-back.  160 texels = 5 whole warps, and a
+// box of 9 x 160 floats is 5760 B = 45 x 128 B, so boxes are 128-byte aligned back to back.  Out-of-range texels of the
+// last tile and planes past the last light are zero-filled on load and clipped on store by the TMA unit.
+constexpr int kBoxW = 160, kBoxes = 3;
+// Texture segments in flight per CTA.  With 2, a warp that is a tile ahead of the slowest warp of its CTA stalls at the
+// next tile's segment (its buffer is released only when the tile two back has been written out): 15 % of all samples
+// in the ncu source view; 3 lets the warps drift like the ring does.
+#ifndef SV_TS_TBUF
+#define SV_TS_TBUF 3
+#endif
+constexpr int kTBuf = SV_TS_TBUF;
+template <typename E>
+__host__ __device__ constexpr int box_stride_bytes() { return (9 * kBoxW * int(sizeof(E)) + 127) / 128 * 128; }
+
+__device__ __forceinline__ void tma_load_box(const CUtensorMap* tm, unsigned dst_smem, int x, int y, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<unsigned long long>(tm)), "r"(x), "r"(y), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, unsigned src_smem, int x, int y) {
+#if !defined(SV_TS_NOSTORE)
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<unsigned long long>(tm)),
+               "r"(x), "r"(y), "r"(src_smem)
+               : "memory");
+#endif
+}
 
 __device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
@@ -1141,9 +1175,9 @@ __device__ __forceinline__ void tma_store_1d(void* dst_gmem, unsigned src_smem, 
 struct TsBars {
   unsigned long long* full;     // [slots] ring slot loaded (TMA complete_tx)
   unsigned long long* empty;    // [slots] ring slot free (CW consumer-warp arrivals, or CW arrivals by the producer after a store-back)
-  unsigned long long* t_full;   // [2] texture segment loaded
-  unsigned long long* t_empty;  // [2] texture segment stored and free
-  unsigned long long* t_done;   // [2] all consumer warps have written the tile's results (CW arrivals)
+  unsigned long long* t_full;   // [kTBuf] texture segment loaded
+  unsigned long long* t_empty;  // [kTBuf] texture segment stored and free
+  unsigned long long* t_done;   // [kTBuf] all consumer warps have written the tile's results (CW arrivals)
 };
 
 template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
@@ -1151,12 +1185,17 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
                                                   const TsBars B, float* stash, float (*s_red)[SH::kCW][4]) {
   typedef typename IoLoad<TGT>::elem elem;
   constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
+  static_assert(SH::kTile == kBoxW * kBoxes, "tile = 3 boxes of 160 texels");
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = P.n_lights, S = P.slots;
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   float pw[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
+  // this thread's column inside a slot: box (5 warps each), position in the box; planes are kBoxW elements apart
+  const int box = tid / kBoxW, wbox = tid - box * kBoxW;
+  const int off_f = box * (box_stride_bytes<float>() / 4) + wbox;                // in floats
+  const int off_e = box * box_stride_bytes<elem>() + wbox * int(sizeof(elem));  // in bytes, target element type
 
   unsigned slot = 0, phase = 0;
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
@@ -1171,15 +1210,15 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
     const long long p = tile * SH::kTile + tid;
     const bool valid = p < P.texels;
-    const unsigned b = t & 1u;
-    float* Tb = T + size_t(b) * 9 * SH::kTile + tid;    // this thread's column of the tile's texture segment
+    const unsigned b = t % unsigned(kTBuf);
+    float* Tb = T + size_t(b) * (SH::kSlotBytes / 4) + off_f;   // this thread's column of the tile's texture segment
 
     // ---- texel prologue ----
     float raw[9], tt[9];
     bool outer[9];
-    mbar_wait(&B.t_full[b], (t >> 1) & 1u);
+    mbar_wait(&B.t_full[b], (t / unsigned(kTBuf)) & 1u);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) raw[k] = valid ? Tb[k * SH::kTile] : 0.f;
+    for (int k = 0; k < 9; ++k) raw[k] = valid ? Tb[k * kBoxW] : 0.f;
     clamp_outer<MODE>(raw, tt, outer);
     Texel<float> tx;
     TexelAux<float> ax;
@@ -1216,12 +1255,12 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
     for (int i0 = 0; i0 < N; i0 += kChunkLights) {
       float in[kChunkLights][3];
       mbar_wait(&B.full[slot], phase);
-      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
+      const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes + off_e);
       if (i0 + kChunkLights <= N) {
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]);
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * kBoxW]);
         }
         release(slot);
         advance();
@@ -1239,7 +1278,7 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
 #pragma unroll
         for (int j = 0; j < kChunkLights; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kBoxW]) : 0.f;
         }
         release(slot);
         advance();
@@ -1263,7 +1302,7 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
       const volatile float* st = stash + tid;
       const volatile float* tv = Tb;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) raw[k] = valid ? tv[k * SH::kTile] : 0.f;
+      for (int k = 0; k < 9; ++k) raw[k] = valid ? tv[k * kBoxW] : 0.f;
 #pragma unroll
       for (int k = 0; k < 7; ++k) ax.dpow[k] = st[k * SH::kTile];
 #pragma unroll
@@ -1280,14 +1319,14 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
     if (MODE == kModeL2Adam) {
       float mk[9], vk[9];
       mbar_wait(&B.full[slot], phase);
-      float* sm = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + tid;
+      float* sm = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + off_f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) mk[k] = sm[k * SH::kTile];
+      for (int k = 0; k < 9; ++k) mk[k] = sm[k * kBoxW];
       advance();                                           // not released: the slot is written back in place below
       mbar_wait(&B.full[slot], phase);
-      float* sv = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + tid;
+      float* sv = reinterpret_cast<float*>(ring + size_t(slot) * SH::kSlotBytes) + off_f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) vk[k] = sv[k * SH::kTile];
+      for (int k = 0; k < 9; ++k) vk[k] = sv[k * kBoxW];
       advance();
 #if SV_STREAM_ONLY
 #pragma unroll
@@ -1311,13 +1350,13 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
 #endif
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        Tb[k * SH::kTile] = raw[k];
-        sm[k * SH::kTile] = mk[k];
-        sv[k * SH::kTile] = vk[k];
+        Tb[k * kBoxW] = raw[k];
+        sm[k * kBoxW] = mk[k];
+        sv[k * kBoxW] = vk[k];
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Tb[k * SH::kTile] = gt[k];
+      for (int k = 0; k < 9; ++k) Tb[k * kBoxW] = gt[k];
     }
     // hand the tile to the producer: generic-proxy writes -> visible to the async proxy, then one arrival per warp
 #if !defined(SV_TS_NOFENCE)
@@ -1344,7 +1383,9 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
   const unsigned C = CL + (MODE == kModeL2Adam ? 2u : 0u);                     // ring chunks per tile
   const unsigned M = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const unsigned total = M * unsigned(P.epochs);
-  float* const out_base = (MODE == kModeL2Adam) ? P.tex : P.out;
+  const CUtensorMap* const tm_store = (MODE == kModeL2Adam) ? &P.tm_tex : &P.tm_out;
+  constexpr unsigned kBoxF = unsigned(box_stride_bytes<float>()), kBoxE = unsigned(box_stride_bytes<elem>());
+  constexpr unsigned kBytesF = 9u * SH::kTile * 4u, kBytesE = 9u * SH::kTile * unsigned(sizeof(elem));   // per slot, OOB included
   unsigned slot = 0, phase = 0;
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
   const bool leader = elect_one();                       // the whole warp runs this role; one lane issues (and owns the bulk groups)
@@ -1353,37 +1394,27 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
   // Write tile `stored` back if all consumer warps are done with it (non-blocking otherwise).
   auto service = [&]() -> bool {
     if (stored >= total) return false;
-    const unsigned b = stored & 1u;
-    if (!__any_sync(0xffffffffu, mbar_test_wait(&B.t_done[b], (stored >> 1) & 1u))) return false;
+    const unsigned b = stored % unsigned(kTBuf);
+    if (!__any_sync(0xffffffffu, mbar_test_wait(&B.t_done[b], (stored / unsigned(kTBuf)) & 1u))) return false;
     const long long tile = (long long)blockIdx.x + (long long)(stored % M) * gridDim.x;
-    const long long p0 = tile * SH::kTile;
-    const unsigned seg = unsigned(min((long long)SH::kTile, P.texels - p0)) * 4u;
-    unsigned src = smem_u32(T) + b * unsigned(SH::kSlotBytes);
-    float* dst = out_base + p0;
-#pragma unroll 1
-    for (int k = 0; k < 9; ++k) {
-      if (leader) tma_store_1d(dst, src, seg);
-      src += SH::kTile * 4;
-      dst += P.stride;
-    }
+    const int x0 = int(tile * SH::kTile);
+    const unsigned src = smem_u32(T) + b * unsigned(SH::kSlotBytes);
     unsigned sm = 0, sv = 0;
     if (MODE == kModeL2Adam) {
       sm = (stored * C + CL) % unsigned(S);
       sv = sm + 1 == unsigned(S) ? 0u : sm + 1;
-      unsigned srcm = smem_u32(ring) + sm * unsigned(SH::kSlotBytes), srcv = smem_u32(ring) + sv * unsigned(SH::kSlotBytes);
-      float* dm = P.m + p0;
-      float* dv = P.v + p0;
-#pragma unroll 1
-      for (int k = 0; k < 9; ++k) {
-        if (leader) {
-          tma_store_1d(dm, srcm, seg);
-          tma_store_1d(dv, srcv, seg);
-        }
-        srcm += SH::kTile * 4; srcv += SH::kTile * 4;
-        dm += P.stride; dv += P.stride;
-      }
     }
     if (leader) {
+#pragma unroll
+      for (int q = 0; q < kBoxes; ++q) tma_store_box(tm_store, src + q * kBoxF, x0 + q * kBoxW, 0);
+      if (MODE == kModeL2Adam) {
+        const unsigned srcm = smem_u32(ring) + sm * unsigned(SH::kSlotBytes), srcv = smem_u32(ring) + sv * unsigned(SH::kSlotBytes);
+#pragma unroll
+        for (int q = 0; q < kBoxes; ++q) {
+          tma_store_box(&P.tm_m, srcm + q * kBoxF, x0 + q * kBoxW, 0);
+          tma_store_box(&P.tm_v, srcv + q * kBoxF, x0 + q * kBoxW, 0);
+        }
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory has been read: the segments may be reused
       mbar_arrive(&B.t_empty[b]);
@@ -1392,7 +1423,6 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
         mbar_arrive_n(&B.empty[sv], SH::kCW);
       }
     }
-    __syncwarp();
     ++stored;
     return true;
   };
@@ -1403,63 +1433,50 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
   unsigned t = 0;
   for (int e = 0; e < P.epochs; ++e) {
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-    const long long p0 = tile * SH::kTile;
-    const unsigned len = unsigned(min((long long)SH::kTile, P.texels - p0));      // texels in this tile (multiple of 4)
-    const unsigned b = t & 1u;
-    wait_serving(&B.t_empty[b], ((t >> 1) & 1u) ^ 1u);
-    if (e > 0 && leader) {
-      // this tile was written back M >= 4 store groups ago; all but the most recent group are complete after this wait
-      asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-    }
-    {
-      unsigned dst = smem_u32(T) + b * unsigned(SH::kSlotBytes);
+    const int x0 = int(tile * SH::kTile);
+    const unsigned b = t % unsigned(kTBuf);
+    wait_serving(&B.t_empty[b], ((t / unsigned(kTBuf)) & 1u) ^ 1u);
+    if (leader) {
+      // e > 0: this tile was written back M >= 4 store groups ago; all but the most recent group are complete after this wait
+      if (e > 0) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+      const unsigned dst = smem_u32(T) + b * unsigned(SH::kSlotBytes);
       const unsigned bar = smem_u32(&B.t_full[b]);
-      const unsigned seg = len * 4u;
-      if (leader) mbar_expect_tx(&B.t_full[b], seg * 9u);
-      const float* src = P.tex + p0;
-      for (int j = 0; j < 9; ++j) {
-        if (leader)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                       "r"(seg), "r"(bar)
-                       : "memory");
-        dst += SH::kTile * 4;
-        src += P.stride;
-      }
+      mbar_expect_tx(&B.t_full[b], kBytesF);
+#pragma unroll
+      for (int q = 0; q < kBoxes; ++q) tma_load_box(&P.tm_tex, dst + q * kBoxF, x0 + q * kBoxW, 0, bar);
     }
-    auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
+    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
       wait_serving(&B.empty[slot], phase ^ 1);
-      unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
-      const unsigned bar = smem_u32(&B.full[slot]);
-      const unsigned seg = len * elem_bytes;
-      if (leader) mbar_expect_tx(&B.full[slot], seg * planes);
-      const unsigned char* src = static_cast<const unsigned char*>(base) + size_t(p0) * elem_bytes;
-      const size_t src_step = size_t(P.stride) * elem_bytes;
-      const unsigned dst_step = unsigned(SH::kTile) * elem_bytes;
-      for (int j = 0; j < planes; ++j) {
-        if (leader)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                       "r"(seg), "r"(bar)
-                       : "memory");
-        dst += dst_step;
-        src += src_step;
+      if (leader) {
+        const unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
+        const unsigned bar = smem_u32(&B.full[slot]);
+        mbar_expect_tx(&B.full[slot], kBytesE);
+#pragma unroll
+        for (int q = 0; q < kBoxes; ++q) tma_load_box(&P.tm_io, dst + q * kBoxE, x0 + q * kBoxW, 3 * i0, bar);
       }
       advance();
-    };
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
-      const int nl = min(kChunkLights, N - i0);
-      fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
       service();
     }
     if (MODE == kModeL2Adam) {
-      fill(P.m, 4, 9);
-      fill(P.v, 4, 9);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        wait_serving(&B.empty[slot], phase ^ 1);
+        if (leader) {
+          const unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
+          const unsigned bar = smem_u32(&B.full[slot]);
+          mbar_expect_tx(&B.full[slot], kBytesF);
+#pragma unroll
+          for (int q = 0; q < kBoxes; ++q) tma_load_box(w == 0 ? &P.tm_m : &P.tm_v, dst + q * kBoxF, x0 + q * kBoxW, 0, bar);
+        }
+        advance();
+      }
     }
   }
   }
   // drain: the last tiles are written back as their consumers finish
   while (stored < total) {
-    const unsigned b = stored & 1u;
-    while (!__any_sync(0xffffffffu, mbar_try_wait_ns(&B.t_done[b], (stored >> 1) & 1u, 2000u))) {
+    const unsigned b = stored % unsigned(kTBuf);
+    while (!__any_sync(0xffffffffu, mbar_try_wait_ns(&B.t_done[b], (stored / unsigned(kTBuf)) & 1u, 2000u))) {
     }
     service();
   }
@@ -1467,19 +1484,19 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
 }
 
 template <int MODE, bool WANT_POW, int TGT, typename SH>
-__global__ void __maxnreg__(SH::kMaxReg) tile_kernel_ts(const Params P) {
+__global__ void __maxnreg__(SH::kMaxReg) tile_kernel_ts(const __grid_constant__ Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: ring [slots] | T [2] | barriers | light geometry 2*N float4 | stash [19 planes]
+  // layout: ring [slots] | T [kTBuf] | barriers | light geometry 2*N float4 | stash [19 planes]
   unsigned char* ring = smem;
   float* T = reinterpret_cast<float*>(smem + size_t(P.slots) * SH::kSlotBytes);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots + 2) * SH::kSlotBytes);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots + kTBuf) * SH::kSlotBytes);
   TsBars B;
   B.full = bars;
   B.empty = B.full + P.slots;
   B.t_full = B.empty + P.slots;
-  B.t_empty = B.t_full + 2;
-  B.t_done = B.t_empty + 2;
-  float4* s_geo = reinterpret_cast<float4*>(B.t_done + 2);
+  B.t_empty = B.t_full + 4;
+  B.t_done = B.t_empty + 4;
+  float4* s_geo = reinterpret_cast<float4*>(B.t_done + 4);
   float* stash = reinterpret_cast<float*>(s_geo + 2 * P.n_lights);
   __shared__ float s_red[2][SH::kCW][4];
 
@@ -1489,7 +1506,7 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel_ts(const Params P) {
       mbar_init(&B.full[s], 1);
       mbar_init(&B.empty[s], SH::kCW);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kTBuf; ++b) {
       mbar_init(&B.t_full[b], 1);
       mbar_init(&B.t_empty[b], 1);
       mbar_init(&B.t_done[b], SH::kCW);
@@ -1785,6 +1802,34 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   return int(cudaGetLastError());
 }
 
+// 2-D TMA descriptor of a planar array: dim0 = texels of the band (contiguous), dim1 = planes (plane stride apart),
+// box = 160 texels x 9 planes.  cuTensorMapEncodeTiled is a pure host-side encoder fetched through the runtime, so the
+// library does not link libcuda.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+static bool make_plane_map(CUtensorMap* tm, const void* base, bool u8, long long texels, long long planes, long long stride_elems) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc || !base) return false;
+  const cuuint64_t eb = u8 ? 1 : 4;
+  const cuuint64_t dims[2] = {cuuint64_t(texels), cuuint64_t(planes)};
+  const cuuint64_t strides[1] = {cuuint64_t(stride_elems) * eb};
+  const cuuint32_t box[2] = {cuuint32_t(kBoxW), 9u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // tile_kernel_ts (results written back by TMA): scalar shape, local outputs only (the peer-push mode keeps per-thread
 // stores to the owner's memory).
 template <int MODE, bool WANT_POW, int TGT, typename SH>
@@ -1795,7 +1840,7 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
   const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
   const size_t stash_bytes = size_t(kStashTs) * SH::kTile * 4;
   const size_t static_smem = 1024;                                     // s_red (static __shared__) + slack
-  const size_t fixed = 2 * size_t(SH::kSlotBytes) + geo + stash_bytes + (2 * 64 + 6) * 8 + 64;
+  const size_t fixed = size_t(kTBuf) * SH::kSlotBytes + geo + stash_bytes + (2 * 64 + 12) * 8 + 64;
   if (size_t(d.smem_optin) < fixed + static_smem + 3 * size_t(SH::kSlotBytes)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
   int slots = env_int("SVBRDF_B200_SLOTS", 0);
   if (slots <= 0) slots = int((size_t(d.smem_optin) - static_smem - fixed) / SH::kSlotBytes);
@@ -1804,8 +1849,16 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
   if (slots > 64) slots = 64;
   if (slots < 3) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
   P.slots = slots;
-  const size_t smem = size_t(slots + 2) * SH::kSlotBytes + size_t(2 * slots + 6) * 8 + geo + stash_bytes + 16;
+  const size_t smem = size_t(slots + kTBuf) * SH::kSlotBytes + size_t(2 * slots + 12) * 8 + geo + stash_bytes + 16;
   if (smem + static_smem > size_t(d.smem_optin)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
+  {
+    const bool u8 = TGT == SVBRDF_TARGET_U8;
+    bool ok = P.texels < (1ll << 31) && make_plane_map(&P.tm_tex, P.tex, false, P.texels, 9, P.stride) &&
+              make_plane_map(&P.tm_io, P.io, u8, P.texels, 3ll * P.n_lights, P.stride);
+    if (MODE == kModeL2Adam) ok = ok && make_plane_map(&P.tm_m, P.m, false, P.texels, 9, P.stride) && make_plane_map(&P.tm_v, P.v, false, P.texels, 9, P.stride);
+    else ok = ok && make_plane_map(&P.tm_out, P.out, false, P.texels, 9, P.stride);
+    if (!ok) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
+  }
   auto kern = tile_kernel_ts<MODE, WANT_POW, TGT, SH>;
   if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
   if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
@@ -1834,7 +1887,9 @@ template <int MODE, bool WANT_POW, int TGT>
 static int launch_tile(Params P, cudaStream_t st) {
   if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
   const bool out_ok = MODE == kModeL2Adam || (reinterpret_cast<uintptr_t>(P.out) & 15) == 0;
-  if (P.push_world == 0 && P.tile_rotate == 0 && out_ok && !env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT) && env_int("SVBRDF_B200_TSTORE", 1))
+  // opt-in (SVBRDF_B200_TSTORE=1): measured 72.3 vs 71.2 us per epoch at 1024^2 x 9 and 1320 vs 1232 us at 2048^2 x 64 against the
+  // per-thread-store kernel below, although it executes 8 % fewer instructions
+  if (P.push_world == 0 && P.tile_rotate == 0 && out_ok && !env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT) && env_int("SVBRDF_B200_TSTORE", 0))
     return launch_tile_ts<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 #if SV_ENABLE_PACKED
   if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);

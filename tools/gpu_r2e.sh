@@ -2,7 +2,7 @@
 # Visit E: warp-uniform producers (elected issue) for both tile kernels: sanity, parity, A/B.
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-TAG=${TAG:-r2e}
+TAG=${TAG:-r2f}
 export SVBRDF_B200_QUIET=1
 echo "== sanity"
 timeout 120 python tools/kernel_bench.py --res 256 --steps 3 --mats 2 --variants "tma1;tma1n;tma1p" 2>&1 | tail -4 | cut -c1-150
