@@ -143,6 +143,36 @@ int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* 
 int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,
                       svbrdf_stream_t stream);
 
+/* ---- texture-map hand-off between resolutions -------------------------------
+ * The reference carries maps from one optim_perpixel call to the next (256 -> 512 -> 1024, run.py:55-56) through
+ * 8-bit PNG files: SvbrdfIO.save_textures_th (svbrdf.py:168-189) quantises, SvbrdfIO.load_textures_th
+ * (svbrdf.py:150-166) decodes and resizes THE BYTES with cv2.resize(INTER_LANCZOS4) (imageio.py:14-15,75-76).
+ * The three entry points below are that round trip on the device, bit for bit (integer/byte work; float steps use
+ * IEEE sqrt/div in the reference's operation order):  encode -> resize -> decode  ==  save -> load(res).
+ * Byte planes are planar, RGB order: [dif r,g,b | nom x,y,z | rgh | spe r,g,b]  (10 planes of rows*cols bytes). */
+#define SVBRDF_MAP_PLANES 10
+
+/* save_textures_th + imwrite: tex [9,rows,cols] (plane_stride elements apart; 0 = rows*cols) -> bytes [10,rows,cols].
+ * clamp_input != 0 applies the caller's textures.clamp(-1,1) (scripts.py:91) first. */
+int svbrdf_maps_encode_u8(const float* tex, int64_t plane_stride, int32_t rows, int32_t cols, int32_t clamp_input,
+                          uint8_t* bytes, svbrdf_stream_t stream);
+
+/* imread + load_textures_th: bytes [10,rows,cols] -> tex [9,rows,cols] in the parameter range [-1,1]. */
+int svbrdf_maps_decode_u8(const uint8_t* bytes, int32_t rows, int32_t cols, float* tex, int64_t plane_stride,
+                          svbrdf_stream_t stream);
+
+/* HOST function: the per-destination-index tables of cv2.resize(INTER_LANCZOS4) on 8-bit data for one axis
+ * (OpenCV imgproc/resize.cpp: interpolateLanczos4, INTER_RESIZE_COEF_BITS = 11): first_tap[d] = floor(fx) - 3 (may be
+ * out of range: taps are clamped to the border), coef[d][8] = saturate_cast<short>(w * 2048).  The caller uploads them. */
+int svbrdf_lanczos4_tables(int32_t src_size, int32_t dst_size, int32_t* first_tap, int16_t* coef);
+
+/* cv2.resize(src, (dst_cols, dst_rows), interpolation=INTER_LANCZOS4) on `planes` independent uint8 planes:
+ * horizontal pass in int32, vertical pass in int32, one rounding shift by 22 bits, replicated borders — bit-identical
+ * to OpenCV.  x_tap/x_coef, y_tap/y_coef: DEVICE copies of the tables above for the two axes. */
+int svbrdf_resize_lanczos4_u8(const uint8_t* src, int32_t planes, int32_t src_rows, int32_t src_cols, uint8_t* dst,
+                              int32_t dst_rows, int32_t dst_cols, const int32_t* x_tap, const int16_t* x_coef,
+                              const int32_t* y_tap, const int16_t* y_coef, svbrdf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

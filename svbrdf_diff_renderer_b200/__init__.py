@@ -10,6 +10,8 @@ from ._native import build_native, lib  # noqa: F401
 from .microfacet import Microfacet  # noqa: F401
 from .optimization import Optim  # noqa: F401
 from .svbrdf import SvbrdfIO, SvbrdfOptim  # noqa: F401
-from .scripts import optim_perpixel, render  # noqa: F401
+from .scripts import optim_perpixel, optim_perpixel_pyramid, render  # noqa: F401
+from . import maps  # noqa: F401
 
-__all__ = ["Microfacet", "Optim", "SvbrdfOptim", "SvbrdfIO", "optim_perpixel", "render", "build_native", "lib"]
+__all__ = ["Microfacet", "Optim", "SvbrdfOptim", "SvbrdfIO", "optim_perpixel", "optim_perpixel_pyramid", "render", "maps",
+           "build_native", "lib"]

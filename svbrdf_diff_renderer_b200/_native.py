@@ -20,7 +20,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsvbrdf_b200.so")
-SOURCES = [os.path.join(CSRC, "svbrdf_kernels.cu")]
+SOURCES = [os.path.join(CSRC, "svbrdf_kernels.cu"), os.path.join(CSRC, "svbrdf_maps.cu")]
 HEADERS = [os.path.join(CSRC, "svbrdf_core.cuh"), os.path.join(_ROOT, "include", "svbrdf_b200.h")]
 
 NVCC_FLAGS = [
@@ -40,6 +40,7 @@ EXPORTS = (
     "svbrdf_abi_version", "svbrdf_error_string", "svbrdf_workspace_bytes", "svbrdf_render_fwd", "svbrdf_render_bwd",
     "svbrdf_l2_grad", "svbrdf_l2_adam_step", "svbrdf_l2_adam_run", "svbrdf_adam_apply",
     "svbrdf_l2_grad_push", "svbrdf_reduce_adam_push",
+    "svbrdf_maps_encode_u8", "svbrdf_maps_decode_u8", "svbrdf_lanczos4_tables", "svbrdf_resize_lanczos4_u8",
 )
 
 
@@ -127,6 +128,10 @@ def lib() -> ctypes.CDLL:
     pp = ctypes.POINTER(Peers)
     L.svbrdf_l2_grad_push.argtypes = [gp, vp, vp, i32, i32, pp, vp, vp, vp]
     L.svbrdf_reduce_adam_push.argtypes = [pp, i64, vp, vp, ap, vp]
+    L.svbrdf_maps_encode_u8.argtypes = [vp, i64, i32, i32, i32, vp, vp]
+    L.svbrdf_maps_decode_u8.argtypes = [vp, i32, i32, vp, i64, vp]
+    L.svbrdf_lanczos4_tables.argtypes = [i32, i32, vp, vp]          # host pointers (numpy buffers)
+    L.svbrdf_resize_lanczos4_u8.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     for name in EXPORTS[3:]:
         getattr(L, name).restype = ctypes.c_int
     if L.svbrdf_abi_version() != 1:

@@ -172,9 +172,11 @@ struct Fm<V2> {
   static SV_HD V2 ex2(const V2& a) { return V2(S::ex2(a.x), S::ex2(a.y)); }
   static SV_HD V2 max(const V2& a, const V2& b) { return V2(S::max(a.x, b.x), S::max(a.y, b.y)); }
   static SV_HD V2 min(const V2& a, const V2& b) { return V2(S::min(a.x, b.x), S::min(a.y, b.y)); }
-  // per component on purpose: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (checked with
-  // cuobjdump), so a packed product is not a "rounded product" once a packed add/sub consumes it
-  static SV_HD V2 mul(const V2& a, const V2& b) { return V2(S::mul(a.x, b.x), S::mul(a.y, b.y)); }
+  // NOTE: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (checked with cuobjdump), so in the
+  // packed two-texel kernel the encoded value is NOT rounded before the target is subtracted: its loss at a rendered
+  // ground truth is ~1e-15 instead of exactly 0.  Splitting the product into two scalar FMULs restores exactness but
+  // costs the packed kernel 5-9 % (register pairing breaks); the packed shape is an opt-in experiment, so it keeps FMUL2.
+  static SV_HD V2 mul(const V2& a, const V2& b) { return a * b; }
 #if defined(__CUDA_ARCH__)
   static SV_D V2 fma(const V2& a, const V2& b, const V2& c) { return f2v(__ffma2_rn(v2f(a), v2f(b), v2f(c))); }
 #else

@@ -65,6 +65,13 @@ def imwrite(im, filename, flag=None, dim=None):
     cv2.imwrite(str(filename), (im * 255).astype("uint8"))
 
 
+def imwrite_u8(im, filename):
+    """Write already-quantised bytes (BGR interleaved or single channel), e.g. from ``maps.encode_u8``."""
+    if im.dtype != np.uint8:
+        raise ValueError("imwrite_u8 takes uint8 arrays")
+    cv2.imwrite(str(filename), im)
+
+
 def imconcat(im_list, size=(2, 2)):
     w, h = size
     return cv2.vconcat([cv2.hconcat([im_list[r * w + c] for c in range(w)]) for r in range(h)])

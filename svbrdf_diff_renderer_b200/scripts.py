@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch as th
 
+from . import maps
 from .microfacet import Microfacet
 from .svbrdf import SvbrdfIO, SvbrdfOptim
 
@@ -46,16 +47,33 @@ def optim_perpixel(json_dir, res, lr, epochs, tex_init, optim_light=False, uint8
         optim_obj.init_from_const()
     elif tex_init == "textures":
         optim_obj.init_from_tex(svbrdf_obj.load_textures_th(svbrdf_obj.reference_dir, res))
+    elif isinstance(tex_init, th.Tensor):
+        # device-side coarse-to-fine hand-off: the previous resolution's maps, quantised, Lanczos-resized and decoded on
+        # the GPU exactly as the reference's save_textures_th -> load_textures_th(res) round trip does through PNG files
+        optim_obj.init_from_tex(maps.handoff(tex_init.to(device), res))
     else:
-        raise ValueError(f"tex_init must be 'random', 'const' or 'textures', got {tex_init!r}")
+        raise ValueError(f"tex_init must be 'random', 'const', 'textures' or a [1,9,r,r] tensor, got {tex_init!r}")
 
     optim_obj.optim(epochs, lr, svbrdf_obj, optim_light)
 
     with th.no_grad():
-        maps = optim_obj.textures.detach().clamp(-1, 1)
-        svbrdf_obj.save_textures_th(maps, svbrdf_obj.optimize_dir)
+        final = optim_obj.textures.detach().clamp(-1, 1)
+        svbrdf_obj.save_textures_th(final, svbrdf_obj.optimize_dir)
         if optim_light:
             print("Optimized light: ", svbrdf_obj.cl[2])
             renderer_obj.update_light(svbrdf_obj.cl[2])
-        svbrdf_obj.save_images_th(renderer_obj.eval(maps), svbrdf_obj.rerender_dir)
+        svbrdf_obj.save_images_th(renderer_obj.eval(final), svbrdf_obj.rerender_dir)
     return optim_obj
+
+
+def optim_perpixel_pyramid(stages, lr, epochs, tex_init="const", optim_light=False, uint8_targets=False):
+    """The reference's coarse-to-fine recipe (run.py:55-56: 256 -> 512 -> 1024, each stage initialised with the previous
+    stage's maps) with the hand-off kept on the device.  ``stages`` is a list of ``(json_dir, res)``; every stage is
+    one ``optim_perpixel`` call (same files written), stage k+1 starts from ``maps.handoff(stage k maps, res)`` — bit
+    for bit what ``tex_init="textures"`` loads when ``reference_dir`` of stage k+1 is ``optimize_dir`` of stage k."""
+    prev, out = tex_init, []
+    for json_dir, res in stages:
+        o = optim_perpixel(json_dir, res, lr, epochs, prev, optim_light, uint8_targets)
+        prev = o.textures.detach()
+        out.append(o)
+    return out

@@ -21,7 +21,8 @@ import numpy as np
 import torch as th
 
 from . import _native as nv
-from .imageio import imread, imread_raw, imwrite, img9to1, tex4to1
+from . import maps
+from .imageio import imread, imread_raw, imwrite, imwrite_u8, img9to1, tex4to1
 from .microfacet import _log
 from .optimization import Optim
 
@@ -197,9 +198,22 @@ class SvbrdfIO:
         self.cl = [self.np_to_th(cam), self.np_to_th(light), self.np_to_th(power)]
         _log("[DONE:SvbrdfIO] Load parameters")
 
-    def load_textures_th(self, textures_dir, res):
+    def load_textures_th(self, textures_dir, res, on_device=None):
+        """svbrdf.py:150-166.  On a CUDA device the decoded PNG bytes are uploaded as they are (10 B per texel) and
+        resized (cv2-exact Lanczos-4) and decoded by the native kernels of ``maps.py``; ``on_device=False`` forces the
+        host path (cv2 + numpy, the reference's own behaviour).  Both give the same maps bit for bit."""
         if not textures_dir.exists():
             raise FileNotFoundError(f"[ERROR:SvbrdfIO:load_textures_th] {textures_dir} is not exists")
+        if on_device is None:
+            on_device = th.device(self.device).type == "cuda"
+        if on_device:
+            arrays = {k: imread_raw(textures_dir / f"{k}.png") for k in ("nom", "dif", "spe", "rgh")}
+            eight_bit = all(a.dtype == np.uint8 for a in arrays.values())
+            if eight_bit and arrays["rgh"].ndim == 2 and all(arrays[k].ndim == 3 and arrays[k].shape[2] == 3 for k in ("nom", "dif", "spe")):
+                planes = maps.png_arrays_to_planes(arrays, self.device)
+                out = maps.decode_u8(maps.resize_lanczos4_u8(planes, res, res))
+                _log("[DONE:SvbrdfIO] Load textures (numbers in range [-1,1])")
+                return out
         normal = imread(textures_dir / "nom.png", "normal", (res, res))
         diffuse = imread(textures_dir / "dif.png", "srgb", (res, res))
         specular = imread(textures_dir / "spe.png", "srgb", (res, res))
@@ -210,7 +224,15 @@ class SvbrdfIO:
         return out.contiguous()
 
     def save_textures_th(self, textures_th, textures_dir):
+        """svbrdf.py:168-189.  CUDA maps are quantised by the native encoder (``maps.encode_u8``: 10 B per texel cross
+        the bus instead of 36) — the PNG files are identical to the host path's."""
         textures_dir.mkdir(parents=True, exist_ok=True)
+        if textures_th.is_cuda and textures_th.dtype == th.float32:
+            for name, arr in maps.planes_to_png_arrays(maps.encode_u8(textures_th.contiguous(), clamp=False)).items():
+                imwrite_u8(arr, textures_dir / f"{name}.png")
+            tex4to1(textures_dir)
+            _log("[DONE:SvbrdfIO] Save textures")
+            return
         hwc = lambda t: self.th_to_np(t.squeeze(0).permute(1, 2, 0))  # noqa: E731
         imwrite(hwc(self.reconstruct_normal(textures_th[:, 3:5])), textures_dir / "nom.png", "normal")
         imwrite(hwc((textures_th[:, 0:3] + 1) / 2), textures_dir / "dif.png", "srgb")
