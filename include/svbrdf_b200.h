@@ -143,6 +143,22 @@ int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* 
 int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,
                       svbrdf_stream_t stream);
 
+/* ---- mode-B consumers: the render as the MaterialGAN latent optimiser and the VGG descriptor loss use it --------------
+ * (materialgan.py:136-147, descriptor.py:65-79, optimization.py:28-29).
+ * Forward: Microfacet.eval, then VGGLoss.normalize — (x - mean[c]) / std[c] per channel, torchvision Normalize — written
+ * to `out` [N,3,rows,res], and, when target != NULL, MSELoss(rendered, target) of the UN-normalised image in loss_out[0]:
+ * one pass instead of render + clone + per-image normalise loop + MSE.  mean/std are HOST float[3]. */
+int svbrdf_render_norm_l2_fwd(const svbrdf_geom_t* geom, const float* tex, const float* mean, const float* std_,
+                              const void* target, int32_t target_dtype, float* out, float* loss_out, void* workspace,
+                              svbrdf_stream_t stream);
+
+/* Backward of the above in one pass: grad_out [N,3,rows,res] is dLoss/d(normalised image) (from the feature network's
+ * backward), l2_grad a DEVICE scalar dLoss/d(loss_out[0]) (NULL or target == NULL: no L2 term).  The upstream of the
+ * render VJP is grad_out/std[c] + l2_grad * 2 (rendered - target) / (N*3*res*res), formed per sample in registers. */
+int svbrdf_render_norm_l2_bwd(const svbrdf_geom_t* geom, const float* tex, const float* std_, const float* grad_out,
+                              const void* target, int32_t target_dtype, const float* l2_grad, float* grad_tex,
+                              float* grad_pow, void* workspace, svbrdf_stream_t stream);
+
 /* ---- texture-map hand-off between resolutions -------------------------------
  * The reference carries maps from one optim_perpixel call to the next (256 -> 512 -> 1024, run.py:55-56) through
  * 8-bit PNG files: SvbrdfIO.save_textures_th (svbrdf.py:168-189) quantises, SvbrdfIO.load_textures_th

@@ -12,6 +12,7 @@ from .optimization import Optim  # noqa: F401
 from .svbrdf import SvbrdfIO, SvbrdfOptim  # noqa: F401
 from .scripts import optim_perpixel, optim_perpixel_pyramid, render  # noqa: F401
 from . import maps  # noqa: F401
+from .descriptor import VGGLoss  # noqa: F401
 
-__all__ = ["Microfacet", "Optim", "SvbrdfOptim", "SvbrdfIO", "optim_perpixel", "optim_perpixel_pyramid", "render", "maps",
+__all__ = ["Microfacet", "Optim", "SvbrdfOptim", "SvbrdfIO", "optim_perpixel", "optim_perpixel_pyramid", "render", "maps", "VGGLoss",
            "build_native", "lib"]

@@ -41,6 +41,7 @@ EXPORTS = (
     "svbrdf_l2_grad", "svbrdf_l2_adam_step", "svbrdf_l2_adam_run", "svbrdf_adam_apply",
     "svbrdf_l2_grad_push", "svbrdf_reduce_adam_push",
     "svbrdf_maps_encode_u8", "svbrdf_maps_decode_u8", "svbrdf_lanczos4_tables", "svbrdf_resize_lanczos4_u8",
+    "svbrdf_render_norm_l2_fwd", "svbrdf_render_norm_l2_bwd",
 )
 
 
@@ -128,6 +129,9 @@ def lib() -> ctypes.CDLL:
     pp = ctypes.POINTER(Peers)
     L.svbrdf_l2_grad_push.argtypes = [gp, vp, vp, i32, i32, pp, vp, vp, vp]
     L.svbrdf_reduce_adam_push.argtypes = [pp, i64, vp, vp, ap, vp]
+    f3 = ctypes.POINTER(ctypes.c_float)
+    L.svbrdf_render_norm_l2_fwd.argtypes = [gp, vp, f3, f3, vp, i32, vp, vp, vp, vp]
+    L.svbrdf_render_norm_l2_bwd.argtypes = [gp, vp, f3, vp, vp, i32, vp, vp, vp, vp, vp]
     L.svbrdf_maps_encode_u8.argtypes = [vp, i64, i32, i32, i32, vp, vp]
     L.svbrdf_maps_decode_u8.argtypes = [vp, i32, i32, vp, i64, vp]
     L.svbrdf_lanczos4_tables.argtypes = [i32, i32, vp, vp]          # host pointers (numpy buffers)

@@ -330,7 +330,10 @@ SV_HD void grads_zero(Grads<T>& g) {
 //   kL2      : `io` holds the target image; accumulates (out - target)^2 and its gradient
 // Gradients are accumulated WITHOUT the constant image-gradient factor (see epilogue).
 // ---------------------------------------------------------------------------------------------
-enum LightMode { kRender = 0, kVjp = 1, kL2 = 2 };
+//   kVjpL2   : `io` holds an upstream dL/d out_c, `tgt` a target image and `l2w` a weight: the upstream is
+//              io_c + l2w * (out_c - tgt_c) — an arbitrary image loss plus an L2 term in one pass (the combined
+//              loss of materialgan.py:141-147); also accumulates (out - tgt)^2
+enum LightMode { kRender = 0, kVjp = 1, kL2 = 2, kVjpL2 = 3 };
 
 template <typename T>
 struct LightGeom {   // per light, texture independent
@@ -429,7 +432,8 @@ SV_D void channels_rg(const float kdp[3], const float Fp[3], float w, float Q, c
 #endif
 
 template <typename T, int MODE, bool WANT_POW>
-SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out[3], Grads<T>& g, T& gw, T& gQ) {
+SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out[3], Grads<T>& g, T& gw, T& gQ,
+                    const T* tgt = nullptr, T l2w = T(0)) {
   typedef Fm<T> F;
   gw = T(0);
   gQ = T(0);
@@ -467,9 +471,9 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
     const T lg = F::lg2(Icl[c]);
     slope[c] = F::ex2(lg * T(1.0 / kGamma - 1.0));
 #if SV_OUT_FROM_SLOPE
-    if (MODE == kL2) o[c] = F::mul(slope[c], Icl[c]);         // Icl^(1/g) = Icl^(1/g - 1) * Icl: a multiplication instead of a MUFU
+    if (MODE == kL2 || MODE == kVjpL2) o[c] = F::mul(slope[c], Icl[c]);   // Icl^(1/g) = Icl^(1/g - 1) * Icl: a multiplication instead of a MUFU
 #else
-    if (MODE == kL2) o[c] = F::ex2(lg * T(1.0 / kGamma));
+    if (MODE == kL2 || MODE == kVjpL2) o[c] = F::ex2(lg * T(1.0 / kGamma));
 #endif
   }
 #endif
@@ -479,6 +483,10 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
       const T diff = o[c] - io[c];
       g.loss = F::fma(diff, diff, g.loss);
       up = diff;
+    } else if (MODE == kVjpL2) {
+      const T diff = o[c] - tgt[c];
+      g.loss = F::fma(diff, diff, g.loss);
+      up = F::fma(diff, l2w, io[c]);
     } else {
       up = io[c];
     }
@@ -498,7 +506,8 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
 //     gv = c (1-k) + k,  q = 4 c^2 + eps,
 // and its gradient is taken through d ln Q.
 template <typename T, int MODE, bool WANT_POW>
-SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
+SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g,
+                             const T* tgt = nullptr, T l2w = T(0)) {
   typedef Fm<T> F;
   const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
   const T vv = F::fma(Vx, Vx, F::fma(Vy, Vy, lg.cz2));
@@ -526,7 +535,7 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
   const T Q = tx.a2 * R0;
   T fp[3], gfp[3], gw, gQ;
 #if SV_PAIR_RG && defined(__CUDA_ARCH__)
-  if (sizeof(T) == 4 && MODE != kRender) {
+  if (sizeof(T) == 4 && (MODE == kVjp || MODE == kL2)) {
     channels_rg<MODE, WANT_POW>(reinterpret_cast<const float*>(tx.kdp), reinterpret_cast<const float*>(tx.Fp), *reinterpret_cast<const float*>(&w),
                                 *reinterpret_cast<const float*>(&Q), reinterpret_cast<const float*>(io), reinterpret_cast<float*>(gfp),
                                 *reinterpret_cast<Grads<float>*>(&g), *reinterpret_cast<float*>(&gw), *reinterpret_cast<float*>(&gQ));
@@ -534,7 +543,7 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
 #endif
   {
     for (int ch = 0; ch < 3; ++ch) fp[ch] = F::fma(Q, tx.Fp[ch], tx.kdp[ch]);
-    channels<T, MODE, WANT_POW>(fp, tx.Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ);
+    channels<T, MODE, WANT_POW>(fp, tx.Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ, tgt, l2w);
   }
   if (MODE == kRender) return;
 
@@ -557,7 +566,8 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
 
 // General light/camera pair.
 template <typename T, int MODE, bool WANT_POW>
-SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
+SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g,
+                               const T* tgt = nullptr, T l2w = T(0)) {
   typedef Fm<T> F;
   // --- geometry (microfacet.py:91-99) ---
   const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
@@ -598,7 +608,7 @@ SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const
     Fp[ch] = F::fma(tx.omsp[ch], sphg, tx.sp[ch]);
     fp[ch] = F::fma(Q, Fp[ch], tx.kdp[ch]);
   }
-  channels<T, MODE, WANT_POW>(fp, Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ);
+  channels<T, MODE, WANT_POW>(fp, Fp, w, Q, io, MODE == kRender ? out : gfp, g, gw, gQ, tgt, l2w);
   if (MODE == kRender) return;
 
   const T QomS = Q * (T(1) - sphg);
@@ -629,9 +639,10 @@ SV_HD void shade_light_general(const Texel<T>& tx, const LightGeom<T>& lg, const
 }
 
 template <typename T, int MODE, bool COLOC, bool WANT_POW>
-SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g) {
-  if (COLOC) shade_light_coloc<T, MODE, WANT_POW>(tx, lg, io, out, g);
-  else shade_light_general<T, MODE, WANT_POW>(tx, lg, io, out, g);
+SV_HD void shade_light(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g,
+                       const T* tgt = nullptr, T l2w = T(0)) {
+  if (COLOC) shade_light_coloc<T, MODE, WANT_POW>(tx, lg, io, out, g, tgt, l2w);
+  else shade_light_general<T, MODE, WANT_POW>(tx, lg, io, out, g, tgt, l2w);
 }
 
 // ---------------------------------------------------------------------------------------------

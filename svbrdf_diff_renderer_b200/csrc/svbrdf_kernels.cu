@@ -124,6 +124,11 @@ struct Params {
   int n_lights;
   float scale;           // constant image-gradient factor
   AdamStep<float> adam;
+  // mode-B consumers (norm_l2_kernel): per-channel normalisation (out - mean)/std of the rendered image, an optional
+  // target for the L2 term and the upstream gradient of the L2 loss value (device scalar)
+  const void* io2;        // target image [N,3] planes (f32 or u8), nullable
+  float aff_mean[3], aff_std[3];
+  const float* l2_up;     // nullable: dLoss/d(l2 loss value)
   // finalisation by the last CTA to finish (tile_kernel)
   double loss_norm;      // 1/(n_total*3*res*res)
   float* loss_out;       // nullable
@@ -478,6 +483,110 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
       for (int w = 0; w < kThreads / 32; ++w) acc += s_red[w][threadIdx.x];
       P.partials[(long long)blockIdx.x * 4 + threadIdx.x] = acc;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// norm_l2_kernel: the render as the mode-B consumers use it (materialgan.py:136-147, descriptor.py:65-79): the image is
+// wanted NORMALISED for the feature network ((x - mean)/std per channel, descriptor.py:65-75) and the image loss is an
+// L2 against the targets (optimization.py:28-29).  Forward: one pass writes the normalised image and the L2 partial
+// sums (instead of render + clone + per-image normalise loop + MSE).  Backward: one pass takes the gradient w.r.t. the
+// normalised image, adds the L2 term's gradient from the target and chains to the textures (instead of 4 image-sized
+// passes + the render VJP).  One thread per texel, direct LDG/STG.
+// ---------------------------------------------------------------------------------------------
+template <bool BWD, bool COLOC, bool WANT_POW, int TGT>
+__device__ __forceinline__ void norm_l2_lights(const Params& P, const float4* __restrict__ s_geo, const Texel<float>& tx, long long p, bool valid,
+                                                Grads<float>& g) {
+  typedef typename IoLoad<TGT>::elem elem;
+  const int N = P.n_lights;
+  const long long step = 3 * P.stride;
+  const float* __restrict__ gsrc = static_cast<const float*>(P.io) + p;           // BWD: upstream gradient of the normalised image
+  const elem* __restrict__ tsrc = static_cast<const elem*>(P.io2) + p;            // target (nullable)
+  float* __restrict__ dst = P.out + p;
+  const bool has_t = P.io2 != nullptr;
+  float l2w = 0.f;
+  if (BWD && has_t && P.l2_up) l2w = __ldg(P.l2_up) * float(2.0 * P.loss_norm);   // d mse / d out = 2 (out - t) / n_elems
+  for (int i = 0; i < N; ++i) {
+    float tg[3] = {0.f, 0.f, 0.f}, up[3] = {0.f, 0.f, 0.f}, o3[3];
+    if (valid && has_t) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tg[c] = IoLoad<TGT>::decode(__ldg(tsrc + c * P.stride));
+    }
+    if (BWD && valid) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) up[c] = __fdiv_rn(__ldg(gsrc + c * P.stride), P.aff_std[c]);   // d((x - mean)/std)/dx
+    }
+    const LightGeom<float> lg = load_geom<COLOC>(s_geo, i);
+    if (BWD) {
+      if (has_t) shade_light<float, kVjpL2, COLOC, WANT_POW>(tx, lg, up, o3, g, tg, l2w);
+      else shade_light<float, kVjp, COLOC, WANT_POW>(tx, lg, up, o3, g);
+    } else {
+      shade_light<float, kRender, COLOC, false>(tx, lg, up, o3, g);
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (has_t) {
+            const float diff = o3[c] - tg[c];
+            g.loss = __fmaf_rn(diff, diff, g.loss);
+          }
+          dst[c * P.stride] = __fdiv_rn(o3[c] - P.aff_mean[c], P.aff_std[c]);    // torchvision Normalize: sub_(mean).div_(std)
+        }
+      }
+    }
+    gsrc += step; tsrc += step; dst += step;
+  }
+}
+
+template <bool BWD, bool WANT_POW, int TGT>
+__global__ void __launch_bounds__(kThreads) norm_l2_kernel(const Params P) {
+  extern __shared__ float4 s_geo[];
+  __shared__ float s_red[kThreads / 32][4];
+  const bool coloc = stage_lights(P, s_geo, threadIdx.x, kThreads);
+  const long long p = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = p < P.texels;
+  const long long pc = valid ? p : 0;
+  float pw[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pw[c] = P.pow[c];
+  float raw[9];
+  bool outer[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { raw[k] = __ldg(P.tex + k * P.stride + pc); outer[k] = true; }
+  Texel<float> tx;
+  TexelAux<float> ax;
+  {
+    const int row = int(pc / P.res);
+    const int col = int(pc - (long long)row * P.res);
+    texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+  }
+  texel_prologue(raw, pw, tx, ax);
+  Grads<float> g;
+  grads_zero(g);
+  if (coloc) norm_l2_lights<BWD, true, WANT_POW, TGT>(P, s_geo, tx, pc, valid, g);
+  else norm_l2_lights<BWD, false, WANT_POW, TGT>(P, s_geo, tx, pc, valid, g);
+  if (BWD) {
+    float gt[9];
+    if (coloc) texel_epilogue<float, true>(tx, ax, pw, g, P.scale, outer, gt);
+    else texel_epilogue<float, false>(tx, ax, pw, g, P.scale, outer, gt);
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) P.out[k * P.stride + p] = gt[k];
+    }
+  }
+  // block partials: L2 sum (forward) / light-power gradient (backward)
+  float r[4] = {valid ? grads_loss(g) : 0.f, valid ? g.pw[0] : 0.f, valid ? g.pw[1] : 0.f, valid ? g.pw[2] : 0.f};
+  warp_reduce4(r);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s_red[warp][c] = r[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) acc += s_red[w][threadIdx.x];
+    P.partials[(long long)blockIdx.x * 4 + threadIdx.x] = acc;
   }
 }
 
@@ -1906,6 +2015,33 @@ static int launch_l2(const Params& P, bool want_pow, int tgt, cudaStream_t st) {
   return SVBRDF_E_UNSUPPORTED;
 }
 
+template <bool BWD>
+static int launch_norm_l2(Params& P, bool want_pow, int tgt, cudaStream_t st) {
+  const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
+  const int blocks = texel_blocks(P);
+#define SV_LAUNCH_NL2(WP, TG)                                                                                       \
+  do {                                                                                                              \
+    auto kern = norm_l2_kernel<BWD, WP, TG>;                                                                        \
+    if (smem > 48 * 1024)                                                                                           \
+      if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e); \
+    kern<<<blocks, kThreads, smem, st>>>(P);                                                                        \
+  } while (0)
+  if (tgt == SVBRDF_TARGET_U8) {
+    if (want_pow) SV_LAUNCH_NL2(true, SVBRDF_TARGET_U8); else SV_LAUNCH_NL2(false, SVBRDF_TARGET_U8);
+  } else if (tgt == SVBRDF_TARGET_F32) {
+    if (want_pow) SV_LAUNCH_NL2(true, SVBRDF_TARGET_F32); else SV_LAUNCH_NL2(false, SVBRDF_TARGET_F32);
+  } else {
+    return SVBRDF_E_UNSUPPORTED;
+  }
+#undef SV_LAUNCH_NL2
+  if (cudaError_t e = cudaGetLastError()) return int(e);
+  if (P.loss_out || P.grad_pow) {
+    finalize_kernel<<<1, 256, 0, st>>>(P, blocks);
+    return int(cudaGetLastError());
+  }
+  return 0;
+}
+
 static double l2_scale(const svbrdf_geom_t* g, int n_total) {
   return 2.0 / (double(n_total) * 3.0 * double(g->res) * double(g->res) * kGamma);
 }
@@ -2070,6 +2206,41 @@ int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* 
   if (blocks > 148 * 8) blocks = 148 * 8;
   reduce_adam_push_kernel<<<int(blocks), 256, 0, stream>>>(Q);
   return int(cudaGetLastError());
+}
+
+int svbrdf_render_norm_l2_fwd(const svbrdf_geom_t* geom, const float* tex, const float* mean, const float* std_, const void* target,
+                              int32_t target_dtype, float* out, float* loss_out, void* workspace, svbrdf_stream_t stream) {
+  if (int e = check_geom(geom)) return e;
+  if (!tex || !out || !mean || !std_ || !workspace) return SVBRDF_E_BADARG;
+  if (loss_out && !target) return SVBRDF_E_BADARG;
+  Params P = base_params(geom);
+  P.tex = const_cast<float*>(tex);
+  P.out = out;
+  P.io2 = target;
+  for (int c = 0; c < 3; ++c) { P.aff_mean[c] = mean[c]; P.aff_std[c] = std_[c]; }
+  P.partials = static_cast<float*>(workspace);
+  P.loss_norm = 1.0 / (double(geom->n_lights) * 3.0 * double(geom->res) * double(geom->res));
+  P.loss_out = loss_out;
+  return launch_norm_l2<false>(P, false, target ? target_dtype : SVBRDF_TARGET_F32, stream);
+}
+
+int svbrdf_render_norm_l2_bwd(const svbrdf_geom_t* geom, const float* tex, const float* std_, const float* grad_out, const void* target,
+                              int32_t target_dtype, const float* l2_grad, float* grad_tex, float* grad_pow, void* workspace,
+                              svbrdf_stream_t stream) {
+  if (int e = check_geom(geom)) return e;
+  if (!tex || !grad_out || !grad_tex || !std_ || !workspace) return SVBRDF_E_BADARG;
+  Params P = base_params(geom);
+  P.tex = const_cast<float*>(tex);
+  P.io = grad_out;
+  P.io2 = (target && l2_grad) ? target : nullptr;
+  P.l2_up = l2_grad;
+  for (int c = 0; c < 3; ++c) { P.aff_mean[c] = 0.f; P.aff_std[c] = std_[c]; }
+  P.out = grad_tex;
+  P.partials = static_cast<float*>(workspace);
+  P.scale = float(1.0 / kGamma);
+  P.loss_norm = 1.0 / (double(geom->n_lights) * 3.0 * double(geom->res) * double(geom->res));
+  P.grad_pow = grad_pow;
+  return launch_norm_l2<true>(P, grad_pow != nullptr, P.io2 ? target_dtype : SVBRDF_TARGET_F32, stream);
 }
 
 int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_t count, const svbrdf_adam_t* adam,

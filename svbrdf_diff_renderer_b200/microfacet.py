@@ -64,6 +64,54 @@ class _RenderFn(th.autograd.Function):
         return (grad_tex if want_tex else None), grad_pow, None
 
 
+class _RenderNormL2Fn(th.autograd.Function):
+    """``textures, light_pow -> (normalised image [N,3,R,R], L2 loss vs targets)`` in one native pass each way: the
+    render as the mode-B consumers use it (materialgan.py:136-147: ``compute_image_loss(rendereds)`` plus
+    ``VGGLoss(rendereds)``, whose first step is the per-channel normalisation of descriptor.py:65-75)."""
+
+    @staticmethod
+    def forward(ctx, textures, light_pow, renderer, targets, mean, std):
+        tex = nv.dev_f32(textures.detach().contiguous(), "textures")
+        pw = nv.dev_f32(light_pow.detach().contiguous(), "light_pow")
+        n, res = renderer.n_of_imgs, renderer.res
+        out = th.empty(n, 3, res, res, dtype=th.float32, device=tex.device)
+        loss = th.zeros((), dtype=th.float32, device=tex.device)
+        tcode = 0
+        if targets is not None:
+            if not targets.is_cuda or not targets.is_contiguous() or tuple(targets.shape) != (n, 3, res, res):
+                raise RuntimeError(f"targets must be a contiguous CUDA tensor [{n},3,{res},{res}]")
+            tcode = nv.target_dtype_code(targets)
+        f3 = ctypes.c_float * 3
+        ctx.mean, ctx.std = f3(*[float(x) for x in mean]), f3(*[float(x) for x in std])
+        geom = renderer._geom(pw)
+        nv.check(nv.lib().svbrdf_render_norm_l2_fwd(ctypes.byref(geom), nv.ptr(tex), ctx.mean, ctx.std, nv.ptr(targets), tcode, nv.ptr(out),
+                                                    nv.ptr(loss) if targets is not None else None, nv.ptr(renderer._workspace()),
+                                                    nv.stream_ptr(tex.device)), "svbrdf_render_norm_l2_fwd")
+        ctx.renderer, ctx.targets, ctx.tcode = renderer, targets, tcode
+        ctx.save_for_backward(tex, pw)
+        return out, loss
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_loss):
+        tex, pw = ctx.saved_tensors
+        renderer = ctx.renderer
+        want_tex, want_pow = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_tex or want_pow):
+            return None, None, None, None, None, None
+        gout = th.zeros_like(tex.new_empty(renderer.n_of_imgs, 3, renderer.res, renderer.res)) if grad_out is None else \
+            nv.dev_f32(grad_out.contiguous(), "grad_out")
+        l2g = None
+        if ctx.targets is not None and grad_loss is not None:
+            l2g = nv.dev_f32(grad_loss.reshape(1).contiguous(), "grad_loss")
+        grad_tex = th.empty_like(tex)
+        grad_pow = th.empty(3, dtype=th.float32, device=tex.device) if want_pow else None
+        geom = renderer._geom(pw)
+        nv.check(nv.lib().svbrdf_render_norm_l2_bwd(ctypes.byref(geom), nv.ptr(tex), ctx.std, nv.ptr(gout), nv.ptr(ctx.targets), ctx.tcode,
+                                                    nv.ptr(l2g), nv.ptr(grad_tex), nv.ptr(grad_pow), nv.ptr(renderer._workspace()),
+                                                    nv.stream_ptr(tex.device)), "svbrdf_render_norm_l2_bwd")
+        return (grad_tex if want_tex else None), grad_pow, None, None, None, None
+
+
 class Microfacet:
     """Cook-Torrance renderer of a planar sample under N point lights (microfacet.py:9-120)."""
 
@@ -120,6 +168,17 @@ class Microfacet:
         if textures.shape[0] != 1 or textures.shape[1] != 9:
             raise RuntimeError(f"textures must be [1,9,{self.res},{self.res}], got {tuple(textures.shape)}")
         return _RenderFn.apply(textures, self._pow, self)
+
+    def eval_normalized(self, textures, mean, std, targets=None):
+        """``eval`` fused with what the mode-B consumers do next (not in the reference API):
+        returns ``((eval(textures) - mean[c]) / std[c], MSELoss(eval(textures), targets))`` — the input of the feature
+        network (descriptor.py:65-79) and the image loss (optimization.py:28-29) — from ONE native pass, differentiable
+        through one native backward pass that takes both upstream gradients.  ``targets`` may be float32 or uint8."""
+        assert (textures.shape[2] == textures.shape[3])
+        assert (self.res == textures.shape[2])
+        if textures.shape[0] != 1 or textures.shape[1] != 9:
+            raise RuntimeError(f"textures must be [1,9,{self.res},{self.res}], got {tuple(textures.shape)}")
+        return _RenderNormL2Fn.apply(textures, self._pow, self, targets, tuple(mean), tuple(std))
 
     # ---- helpers kept for API compatibility (no caller outside eval in the reference) ----------
     def GGX(self, cos_h, alpha):

@@ -144,6 +144,36 @@ class SvbrdfOptim(Optim):
             pw.requires_grad_(False)
         return self.losses
 
+    def optim_with_features(self, epochs, lr, feature_loss, feature_weight=0.1, optim_light=False):
+        """Per-pixel Adam on the combined loss of the reference's second workflow (materialgan.py:141-147):
+        ``MSELoss(rendered, targets) + feature_weight * VGGLoss(rendered)`` — BASELINE configs[1] "L2 + descriptor loss".
+        The render, the descriptor's input normalisation and the L2 term are one native kernel each way
+        (``Microfacet.eval_normalized``); the feature network is torch/cuDNN.  ``feature_loss`` is a
+        ``descriptor.VGGLoss`` whose ``load(targets)`` has been called.  Returns ``(image losses, feature losses)``."""
+        r = self.renderer_obj
+        params = [self.textures]
+        pw = None
+        if optim_light:
+            pw = r._pow.detach().clone().requires_grad_(True)
+            params.append(pw)
+        self.optimizer = th.optim.Adam(params, lr=lr, betas=(0.9, 0.999))
+        li, lf = [], []
+        for _ in range(epochs):
+            if pw is not None:
+                r.update_light(pw)
+            norm, l2 = r.eval_normalized(self.textures.clamp(-1, 1), feature_loss.mean, feature_loss.std, self.targets)
+            feat = feature_loss.forward_normalized(norm) * feature_weight
+            li.append(l2.detach())
+            lf.append(feat.detach())
+            self.optimizer.zero_grad()
+            (l2 + feat).backward()
+            self.optimizer.step()
+        if pw is not None:
+            pw.requires_grad_(False)
+        self.losses = th.stack(li).tolist() if li else []
+        self.losses_feature = th.stack(lf).tolist() if lf else []
+        return self.losses, self.losses_feature
+
     def _dump(self, svbrdf_obj, tmp_dir, epoch, epochs):
         """svbrdf.py:74-83: loss curve, the four maps and the N re-renders."""
         this_dir = tmp_dir / f"{epoch}"
