@@ -201,7 +201,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -415,7 +415,7 @@ def run_b200_arm(args):
             "gpu_launches": gpu_launches,
             "gpu_launches_what": "tile_kernel<L2Adam> launches in the timed region: one persistent launch per material and <=64 epochs (loss reduction fused: last CTA finalises each epoch)",
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -478,8 +478,27 @@ def view_sharded_bench(args, dev, world, rank, barrier):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # stdout carries exactly one JSON line: everything else any library writes to fd 1 during the run (NCCL prints
+    # "NCCL version ..." there on communicator creation, whatever NCCL_DEBUG_FILE says) is sent to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
