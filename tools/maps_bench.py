@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Times the map hand-off kernels (encode / Lanczos-4 resize / decode) against their HBM floor and against the host
-path they replace (cv2 + numpy + PNG-free: only the arithmetic, not the file I/O).  Development/measurement tool:
+path they replace (the PNG round trip through cv2 + numpy).  Development/measurement tool:
 
     python tools/maps_bench.py [--res 1024]      # hand-off res -> 2*res
 """
@@ -57,21 +57,28 @@ def main():
     rows["decode"] = (us, (10 + 36) * R * R)
     us = timed(lambda: maps.handoff(nxt(pool), R), a.reps)
     rows["handoff (3 launches)"] = (us, (36 + 10) * r * r + 10 * (r * r + R * R) + (10 + 36) * R * R)
-    # host path: the same arithmetic with cv2 + numpy (no PNG compression, no disk)
-    import cv2
-    from oracle import maps_port as mp
-    t_host = pool[0][0].clamp(-1, 1).cpu().numpy()
-    t0 = time.perf_counter()
-    b = mp.encode_maps_u8(t_host)
-    up = np.stack([cv2.resize(b[i], (R, R), interpolation=cv2.INTER_LANCZOS4) for i in range(10)])
-    out = mp.decode_maps_u8(up)
-    host_ms = (time.perf_counter() - t0) * 1e3
-    res = {"res_in": r, "res_out": R, "host_cv2_numpy_ms": round(host_ms, 2), "peak_GBs": a.peak, "kernels": {}}
+    # host path: what the reference does — SvbrdfIO.save_textures_th -> PNG files -> load_textures_th(dir, 2r) with cv2 and
+    # numpy on the host (svbrdf.py:150-189), here through this package's own host route (on_device=False), files on /tmp
+    import pathlib
+    import tempfile
+
+    import svbrdf_diff_renderer_b200 as pkg
+    io = pkg.SvbrdfIO.__new__(pkg.SvbrdfIO)
+    io.device = th.device("cpu")
+    t_host = pool[0].clamp(-1, 1).cpu()
+    with tempfile.TemporaryDirectory() as d:
+        d = pathlib.Path(d)
+        t0 = time.perf_counter()
+        io.save_textures_th(t_host, d)
+        out = io.load_textures_th(d, R, on_device=False)
+        host_ms = (time.perf_counter() - t0) * 1e3
+    assert th.equal(out, maps.handoff(pool[0], R).cpu()), "device hand-off differs from the host round trip"
+    res = {"res_in": r, "res_out": R, "host_png_round_trip_ms": round(host_ms, 2), "peak_GBs": a.peak, "kernels": {}}
     for name, (us, nbytes) in rows.items():
         gbs = nbytes / (us * 1e-6) / 1e9
         res["kernels"][name] = {"us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2), "GBs": round(gbs, 1), "frac_of_peak": round(gbs / a.peak, 3)}
         print(f"{name:24s} {us:9.2f} us  {nbytes / 1e6:8.2f} MB  {gbs:8.1f} GB/s  {gbs / a.peak * 100:5.1f} % of measured HBM")
-    print(f"host cv2+numpy (arithmetic only): {host_ms:.1f} ms")
+    print(f"host PNG round trip (save_textures_th + load_textures_th, cv2/numpy): {host_ms:.1f} ms; device result identical")
     print(json.dumps(res))
 
 
