@@ -152,11 +152,42 @@ struct Params {
   // (with identical sweeps all ranks would hit one owner's NVLink port at a time: measured 5.0 instead of 2.8 ms
   // for the gradient kernel on 8 GPUs).
   long long tile_rotate;
+  long long span;         // tile_kernel: texels per CTA (contiguous range), 0 = round-robin tiles (see TileMap)
 };
 
 __device__ __forceinline__ long long rotate_tile(long long tile, long long rot, long long n_tiles) {
   const long long t = tile + rot;
   return t >= n_tiles ? t - n_tiles : t;
+}
+// Which texels a CTA of tile_kernel owns.  span == 0: tiles dealt round-robin (tile = cta + j * grid; the peer-sharded
+// modes need tile-aligned ownership).  span > 0: ONE contiguous range of `span` texels per CTA, cut into tiles with a
+// partial last tile — every CTA then carries the same load (ceil(texels/grid) texels) instead of floor or ceil of
+// tiles/grid whole tiles: at 1024^2 (2185 tiles on 148 CTAs) 113 CTAs had 15 tiles and 35 had 14; at 512^2 it was 4 vs 3.
+struct TileMap {
+  long long lo, hi;       // span mode: this CTA's range
+  unsigned count;         // tiles of this CTA per epoch
+  bool spans;
+};
+template <int TILE>
+__device__ __forceinline__ TileMap tile_map(const Params& P, long long span, long long n_tiles) {
+  TileMap m;
+  m.spans = span > 0;
+  if (m.spans) {
+    m.lo = (long long)blockIdx.x * span;
+    m.hi = m.lo + span < P.texels ? m.lo + span : P.texels;
+    m.count = m.hi > m.lo ? unsigned((m.hi - m.lo + TILE - 1) / TILE) : 0u;
+  } else {
+    m.lo = 0;
+    m.hi = P.texels;
+    m.count = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  }
+  return m;
+}
+// first texel of the CTA's j-th tile
+template <int TILE>
+__device__ __forceinline__ long long tile_first(const TileMap& m, const Params& P, unsigned j, long long n_tiles) {
+  if (m.spans) return m.lo + (long long)j * TILE;
+  return rotate_tile((long long)blockIdx.x + (long long)j * gridDim.x, P.tile_rotate, n_tiles) * TILE;
 }
 constexpr int kMaxEpochs = 64;          // per launch
 constexpr int kRowsPerEpoch = 4096;     // workspace rows ([loss, gpow x3]) per epoch: one per consumer warp
@@ -684,7 +715,8 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
 
   // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
-  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const TileMap tmap = tile_map<SH::kTile>(P, P.span, n_tiles);
+  const unsigned my_tiles = tmap.count;
   const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
   unsigned tiles_finished = 0;
   for (int e = 0; e < P.epochs; ++e) {
@@ -692,10 +724,11 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   adam_e.step_size = P.step_size[e];
   adam_e.inv_sqrt_bc2 = P.inv_sqrt_bc2[e];
   float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long rtile = rotate_tile(tile, P.tile_rotate, n_tiles);
-    const long long p = rtile * SH::kTile + tid;
-    const bool valid = p < P.texels;
+  for (unsigned jt = 0; jt < my_tiles; ++jt) {
+    const long long p0t = tile_first<SH::kTile>(tmap, P, jt, n_tiles);
+    const long long rtile = p0t / SH::kTile;                  // round-robin mode only (peer-push ownership)
+    const long long p = p0t + tid;
+    const bool valid = p < tmap.hi;
 
     // ---- texel prologue ----
     float raw[9], t[9];
@@ -960,7 +993,8 @@ __device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __
   };
 
   // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
-  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const TileMap tmap = tile_map<SH::kTile>(P, P.span, n_tiles);
+  const unsigned my_tiles = tmap.count;
   const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
   unsigned tiles_finished = 0;
   for (int e = 0; e < P.epochs; ++e) {
@@ -968,10 +1002,9 @@ __device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __
   adam_e.step_size = P.step_size[e];
   adam_e.inv_sqrt_bc2 = P.inv_sqrt_bc2[e];
   float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long rtile = rotate_tile(tile, P.tile_rotate, n_tiles);
-    const long long p = rtile * SH::kTile + 2 * tid;         // first of this thread's two texels
-    const bool valid = p < P.texels;                          // texels % 4 == 0: both or neither
+  for (unsigned jt = 0; jt < my_tiles; ++jt) {
+    const long long p = tile_first<SH::kTile>(tmap, P, jt, n_tiles) + 2 * tid;   // first of this thread's two texels
+    const bool valid = p < tmap.hi;                           // range ends are multiples of 4: both or neither
 
     // ---- texel prologue ----
     T raw[9], t[9];
@@ -1150,10 +1183,10 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
   auto advance = [&]() { if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
   const bool leader = elect_one();                       // the whole warp runs this role; one lane issues
 
-  const unsigned my_tiles = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const TileMap tmap = tile_map<SH::kTile>(P, P.span, n_tiles);
+  const unsigned my_tiles = tmap.count;
   for (int e = 0; e < P.epochs; ++e) {
-  unsigned local = 0;
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+  for (unsigned local = 0; local < my_tiles; ++local) {
     if (e > 0) {
       // this tile was written by this CTA's consumers in epoch e-1: wait until every warp has stored (and fenced) it
       const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
@@ -1162,8 +1195,8 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
         while (!__any_sync(0xffffffffu, s_done[w] >= need)) {
         }
     }
-    const long long p0 = rotate_tile(tile, P.tile_rotate, n_tiles) * SH::kTile;
-    const unsigned len = unsigned(min((long long)SH::kTile, P.texels - p0));      // texels in this tile (multiple of 4)
+    const long long p0 = tile_first<SH::kTile>(tmap, P, local, n_tiles);
+    const unsigned len = unsigned(min((long long)SH::kTile, tmap.hi - p0));       // texels in this tile (multiple of 4)
     auto fill = [&](const void* base, unsigned elem_bytes, int planes) {
       // `planes` plane segments of `len` elements each, starting at element p0 of consecutive planes of `base`
       mbar_wait_uniform(&empty[slot], phase ^ 1);
@@ -1893,9 +1926,29 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   long long grid = (long long)d.sms * ctas_per_sm;
   if (grid > n_tiles) grid = n_tiles;
+  // equal load per CTA: one contiguous range of ceil(texels/grid) texels (rounded to 32) instead of whole tiles dealt
+  // round-robin; the peer-sharded modes keep tile-aligned ownership
+  P.span = 0;
+  // measured (profiles/r01_s2_variants_spans.txt): 72.3 -> 71.3 us at 1024^2 x 9, 265.9 -> 264.0 us at 2048^2 x 9, but 23.6 -> 26.0 us
+  // at 512^2 (3.7 tiles per CTA: a partial tile costs almost a whole tile's latency), hence only from 8 tiles per CTA up
+  if (P.push_world == 0 && P.tile_rotate == 0 && n_tiles >= 8 * grid && env_int("SVBRDF_B200_SPANS", 1)) {
+    const long long ctas = (long long)d.sms * ctas_per_sm;
+    long long span = (P.texels + ctas - 1) / ctas;
+    span = (span + 31) / 32 * 32;
+    if (span < 32 * 4) span = 32 * 4;                                   // at least 4 warps' worth per CTA
+    P.span = span;
+    grid = (P.texels + span - 1) / span;
+  }
+  // fewest tiles any CTA gets (span mode: the last CTA takes what is left)
+  long long tiles_per_cta = n_tiles / grid;
+  if (P.span) {
+    const long long last = P.texels - (grid - 1) * P.span;
+    tiles_per_cta = (last + SH::kTile - 1) / SH::kTile;
+    if (grid > 1 && (P.span + SH::kTile - 1) / SH::kTile < tiles_per_cta) tiles_per_cta = (P.span + SH::kTile - 1) / SH::kTile;
+  }
   P.counters = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
   if (grid > kRowsPerEpoch) return launch_texel<MODE, WANT_POW, TGT>(P, st);
-  if (P.epochs > 1 && n_tiles / grid < 3) {                           // too few tiles per CTA for the lagging publication: one launch per epoch
+  if (P.epochs > 1 && tiles_per_cta < 3) {                            // too few tiles per CTA for the lagging publication: one launch per epoch
     Params Q = P;
     for (int e = 0; e < P.epochs; ++e) {
       Q.epochs = 1;
