@@ -48,7 +48,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-MODE_RENDER, MODE_VJP, MODE_L2, MODE_ADAM = 0, 1, 2, 3
+MODE_RENDER, MODE_VJP, MODE_L2, MODE_ADAM, MODE_VJP_L2 = 0, 1, 2, 3, 4
 
 
 def adam_scalars(step, lr, b1=0.9, b2=0.999, eps=1e-8):
@@ -80,7 +80,7 @@ def run(mode, tex, cam, light, power, size, res, io=None, dtype=np.float32, colo
         colocated = bool(np.array_equal(cam_a, light_a))
     io_a = None if io is None else np.ascontiguousarray(io, dtype=dtype)
     out = np.zeros((n, 3, rows, w), dtype=dtype) if mode == MODE_RENDER else None
-    grad_tex = np.zeros((9, rows, w), dtype=dtype) if mode in (MODE_VJP, MODE_L2) else None
+    grad_tex = np.zeros((9, rows, w), dtype=dtype) if mode in (MODE_VJP, MODE_L2, MODE_VJP_L2) else None
     grad_pow = np.zeros(3, dtype=dtype) if mode != MODE_RENDER else None
     loss = ctypes.c_double(0.0)
     adam_a = None if adam is None else np.ascontiguousarray(adam, dtype=np.float64)

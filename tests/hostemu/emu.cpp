@@ -22,7 +22,8 @@ LightGeom<T> geom(const T* cam, const T* light, int i) {
   return g;
 }
 
-// mode: 0 render, 1 vjp, 2 l2 grad, 3 l2 + adam
+// mode: 0 render, 1 vjp, 2 l2 grad, 3 l2 + adam, 4 vjp + l2 term (LightMode kVjpL2: `io` upstream gradient, `m` doubles
+// as the target image and adam[0] as the L2 weight — the arguments of svbrdf_render_norm_l2_bwd's inner loop)
 template <typename T, bool COLOC>
 void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size, int res, int row0, int rows, int W,
          int N, int n_total, const T* io, T* out, T* grad_tex, T* grad_pow, double* loss, int outer_clamp, T* m, T* v,
@@ -30,7 +31,7 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
   const size_t plane = size_t(rows) * W;
   double loss_acc = 0.0, gp_acc[3] = {0, 0, 0};
   T scale;
-  if (mode == 1) scale = T(1.0 / kGamma);
+  if (mode == 1 || mode == 4) scale = T(1.0 / kGamma);
   else scale = T(2.0 / (double(n_total) * 3.0 * double(res) * double(res) * kGamma));
   for (int r = 0; r < rows; ++r) {
     for (int c = 0; c < W; ++c) {
@@ -63,6 +64,10 @@ void run(int mode, T* tex, const T* cam, const T* light, const T* pw, float size
           for (int ch = 0; ch < 3; ++ch) out[(size_t(i) * 3 + ch) * plane + p] = o3[ch];
         } else if (mode == 1) {
           shade_light<T, kVjp, COLOC, true>(tx, lg, in3, o3, g);
+        } else if (mode == 4) {
+          T tg[3];
+          for (int ch = 0; ch < 3; ++ch) tg[ch] = m[(size_t(i) * 3 + ch) * plane + p];
+          shade_light<T, kVjpL2, COLOC, true>(tx, lg, in3, o3, g, tg, T(adam[0]));
         } else {
           shade_light<T, kL2, COLOC, true>(tx, lg, in3, o3, g);
         }

@@ -85,13 +85,54 @@ def test_row_band_equals_full():
 
 
 def test_u8_division_is_correctly_rounded():
-    """The in-kernel u8 decode (q = b*r; q += fma(-q,255,b)*r) must equal float32(b)/255 bit for bit."""
-    b = np.arange(256, dtype=np.float32)
-    r = np.float32(1.0) / np.float32(255.0)
-    q = b * r
-    resid = (b.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)      # fma(-q,255,b): exact in fp64
-    fixed = (q.astype(np.float64) + resid.astype(np.float64) * np.float64(r)).astype(np.float32)
-    assert np.array_equal(fixed, b / np.float32(255.0))
+    """The in-kernel u8 decode q = fma(b, hi, b*lo) with hi + lo = 1/255 must equal float32(b)/255 bit for bit
+    (exact rational arithmetic: b*hi is exact inside the FMA, so the only roundings are b*lo and the FMA's)."""
+    from fractions import Fraction
+    hi, lo = np.float32(float.fromhex("0x1.010102p-8")), np.float32(float.fromhex("-0x1.fdfdfep-33"))
+    assert hi == np.float32(1.0 / 255.0) and lo == np.float32(1.0 / 255.0 - float(hi))
+
+    def rn32(fr):                                   # round a positive Fraction to the nearest float32, ties to even
+        e = 0
+        while Fraction(2) ** e > fr:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= fr:
+            e += 1
+        q = fr / Fraction(2) ** (e - 23)
+        n, rem = divmod(q.numerator, q.denominator)
+        if 2 * rem > q.denominator or (2 * rem == q.denominator and n % 2):
+            n += 1
+        return np.float32(float(Fraction(n) * Fraction(2) ** (e - 23)))
+
+    for b in range(1, 256):
+        t = np.float32(np.float32(b) * lo)
+        assert rn32(Fraction(b) * Fraction(float(hi)) + Fraction(float(t))) == np.float32(b) / np.float32(255.0), b
+
+
+@pytest.mark.parametrize("name", ["coloc_32x9", "offaxis_32x9"])
+def test_vjp_with_l2_term_matches_oracle(name):
+    """LightMode kVjpL2 (the inner loop of svbrdf_render_norm_l2_bwd): upstream = g + w * (render - target), formed per
+    sample in registers, against the oracle's VJP of the same upstream (oracle/torch_port.image_grad)."""
+    import torch as th
+    from oracle import torch_port as tp
+    g = parity.golden(name)
+    res, n = int(g["res"]), g["cam"].shape[0]
+    tex = np.clip(g["tex0"][0], -1, 1).astype(np.float64)
+    sc = tp.Scene(res, th.from_numpy(g["cam"]).double(), th.from_numpy(g["light"]).double(), th.from_numpy(g["power_render"]).double(),
+                  float(g["size"]), th.float64)
+    img = tp.shade(sc, th.from_numpy(tex)[None])
+    w = 0.37 * 2.0 / (n * 3 * res * res)
+    target = g["target"].astype(np.float64)
+    up = g["grad_img"].astype(np.float64)
+    ref = tp.image_grad(sc, th.from_numpy(tex)[None], th.from_numpy(up) + w * (img - th.from_numpy(target)))
+    ref_tex = (ref[0] if isinstance(ref, (tuple, list)) else ref).numpy().reshape(9, res, res)
+    out = E.run(E.MODE_VJP_L2, tex, *_args(g), io=up, dtype=np.float64, m=np.ascontiguousarray(target),
+                adam=np.array([w, 0, 0, 0, 0, 0], dtype=np.float64))
+    assert parity.max_err(out["grad_tex"], ref_tex) < 1e-10
+    assert out["loss"] == pytest.approx(float(((img.numpy() - target) ** 2).mean()), rel=1e-12)
+    # float instantiation within the usual gradient tolerance of the double result
+    o32 = E.run(E.MODE_VJP_L2, tex.astype(np.float32), *_args(g), io=up.astype(np.float32), dtype=np.float32,
+                m=np.ascontiguousarray(target.astype(np.float32)), adam=np.array([w, 0, 0, 0, 0, 0], dtype=np.float64))
+    assert parity.pass_fraction(o32["grad_tex"], ref_tex, parity.RTOL_GRAD) > 0.995
 
 
 @pytest.mark.parametrize("name", ["coloc_32x9", "edges_offaxis_32x9", "light_32x9"])
