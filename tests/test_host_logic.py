@@ -103,3 +103,43 @@ def test_optim_base_class_api():
         base.load_targets(None)
     with pytest.raises(NotImplementedError):
         base.optim(1, 0.1, None, False)
+
+
+def test_vggloss_drop_in_matches_oracle_on_cpu():
+    """descriptor.VGGLoss is plain torch: on the CPU it must agree with the oracle's op-for-op restatement of the
+    reference class (descriptor.py:7-79) — broadcast normalisation == per-image loop, same hooks, same weighting."""
+    import pytest
+    pytest.importorskip("torchvision")
+    import torch as th
+    from torchvision.models import vgg19
+
+    from oracle import descriptor_port as dp
+    from svbrdf_diff_renderer_b200.descriptor import VGGLoss
+    th.manual_seed(11)
+    mine = VGGLoss(th.device("cpu"), net=vgg19(weights=None).features)
+    net = dp.seeded_vgg_features(11)
+    x = th.rand(2, 3, 32, 32, generator=th.Generator().manual_seed(1))
+    y = th.rand(2, 3, 32, 32, generator=th.Generator().manual_seed(2))
+    assert th.equal(mine.normalize(x), dp.normalize(x))
+    mine.load(y)
+    ref = float(dp.vgg_loss(net, x, dp.feature_vector(net, dp.normalize(y))))
+    assert float(mine(x)) == pytest.approx(ref, rel=1e-6)
+    assert float(mine.forward_normalized(mine.normalize(x))) == pytest.approx(ref, rel=1e-6)
+    assert mine.compute_feature_vector(mine.normalize(x), is_gram=True).numel() == sum((2 * c) ** 2 for c in (64, 64, 256, 512))
+
+
+def test_map_plane_layout_round_trip():
+    """maps.planes_to_png_arrays / png_arrays_to_planes: planar RGB byte planes <-> the BGR-interleaved arrays cv2 handles."""
+    import numpy as np
+    import torch as th
+
+    from svbrdf_diff_renderer_b200 import maps
+    planes = th.from_numpy(np.random.default_rng(0).integers(0, 256, (10, 6, 5), dtype=np.uint8))
+    arrays = maps.planes_to_png_arrays(planes)
+    assert arrays["dif"].shape == (6, 5, 3) and arrays["rgh"].shape == (6, 5)
+    assert np.array_equal(arrays["dif"][:, :, 0], planes[2].numpy()) and np.array_equal(arrays["nom"][:, :, 2], planes[3].numpy())
+    back = maps.png_arrays_to_planes(arrays, th.device("cpu"))
+    assert th.equal(back, planes)
+    import pytest
+    with pytest.raises(RuntimeError, match="CUDA"):
+        maps.encode_u8(th.zeros(9, 4, 4))
