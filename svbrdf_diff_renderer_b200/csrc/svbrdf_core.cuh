@@ -66,6 +66,7 @@ struct Fm<float> {
   static SV_D float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static SV_D float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
   static SV_D float mul(float a, float b) { return __fmul_rn(a, b); }     // a rounded product the compiler may not contract into an FMA
+  static SV_D float sub(float a, float b) { return __fsub_rn(a, b); }     // a - b that never absorbs the product a came from
   static SV_D float max(float a, float b) { return fmaxf(a, b); }
   static SV_D float min(float a, float b) { return fminf(a, b); }
 #else
@@ -95,6 +96,7 @@ struct Fm<float> {
   static SV_HD float ex2(float x) { return jitter(std::exp2(x), false, 16); }
   static SV_HD float fma(float a, float b, float c) { return std::fma(a, b, c); }
   static SV_HD float mul(float a, float b) { return a * b; }
+  static SV_HD float sub(float a, float b) { return a - b; }
   static SV_HD float max(float a, float b) { return a > b ? a : b; }
   static SV_HD float min(float a, float b) { return a < b ? a : b; }
 #endif
@@ -117,6 +119,7 @@ struct Fm<double> {
   static SV_HD double ex2(double x) { return ::exp2(x); }
   static SV_HD double fma(double a, double b, double c) { return ::fma(a, b, c); }
   static SV_HD double mul(double a, double b) { return a * b; }
+  static SV_HD double sub(double a, double b) { return a - b; }
   static SV_HD double max(double a, double b) { return a > b ? a : b; }
   static SV_HD double min(double a, double b) { return a < b ? a : b; }
 };
@@ -172,15 +175,23 @@ struct Fm<V2> {
   static SV_HD V2 ex2(const V2& a) { return V2(S::ex2(a.x), S::ex2(a.y)); }
   static SV_HD V2 max(const V2& a, const V2& b) { return V2(S::max(a.x, b.x), S::max(a.y, b.y)); }
   static SV_HD V2 min(const V2& a, const V2& b) { return V2(S::min(a.x, b.x), S::min(a.y, b.y)); }
-  // NOTE: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (checked with cuobjdump), so in the
-  // packed two-texel kernel the encoded value is NOT rounded before the target is subtracted: its loss at a rendered
-  // ground truth is ~1e-15 instead of exactly 0.  Splitting the product into two scalar FMULs restores exactness but
-  // costs the packed kernel 5-9 % (register pairing breaks); the packed shape is an opt-in experiment, so it keeps FMUL2.
+  // NOTE: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (checked with cuobjdump); where the
+  // product must be rounded before a subtraction (`encoded - target`), the subtraction is written with sub() below.
   static SV_HD V2 mul(const V2& a, const V2& b) { return a * b; }
 #if defined(__CUDA_ARCH__)
   static SV_D V2 fma(const V2& a, const V2& b, const V2& c) { return f2v(__ffma2_rn(v2f(a), v2f(b), v2f(c))); }
+  // a - b as two scalar subtractions (opaque to the vectoriser): a packed product followed by a scalar FADD is not
+  // contracted, so `encoded - target` sees the encoded value rounded exactly like the render kernel writes it and the L2
+  // forward of a rendered target is exactly zero in the packed instantiations too.
+  static SV_D V2 sub(const V2& a, const V2& b) {
+    V2 r;
+    asm("sub.rn.f32 %0, %1, %2;" : "=f"(r.x) : "f"(a.x), "f"(b.x));
+    asm("sub.rn.f32 %0, %1, %2;" : "=f"(r.y) : "f"(a.y), "f"(b.y));
+    return r;
+  }
 #else
   static SV_HD V2 fma(const V2& a, const V2& b, const V2& c) { return V2(S::fma(a.x, b.x, c.x), S::fma(a.y, b.y, c.y)); }
+  static SV_HD V2 sub(const V2& a, const V2& b) { return V2(a.x - b.x, a.y - b.y); }
 #endif
 };
 
@@ -480,11 +491,11 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
   for (int c = 0; c < 3; ++c) {
     T up;
     if (MODE == kL2) {
-      const T diff = o[c] - io[c];
+      const T diff = F::sub(o[c], io[c]);
       g.loss = F::fma(diff, diff, g.loss);
       up = diff;
     } else if (MODE == kVjpL2) {
-      const T diff = o[c] - tgt[c];
+      const T diff = F::sub(o[c], tgt[c]);
       g.loss = F::fma(diff, diff, g.loss);
       up = F::fma(diff, l2w, io[c]);
     } else {

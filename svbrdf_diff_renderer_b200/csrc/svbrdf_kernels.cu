@@ -45,14 +45,21 @@ constexpr int kPrefetch = 2;           // texel_kernel: lights of io data in fli
 //    registers: 80.0 vs 89.1 / 84.7 / 89.7 us per step.
 //  * packed (LANES = 2): two texels per thread in FP32x2 registers (FFMA2/FMUL2/FADD2), 7+1 warps at up to
 //    255 registers.
-template <int CW, int LANES, int MAXNREG>
+//  * CHUNK = lights per ring slot: the consumer loads the targets of CHUNK lights, releases the slot and shades them
+//    in one unrolled, unguarded block (CHUNK independent dependency chains interleave).  Measured (profiles/
+//    r01_s3_variants_chunk_lights.txt): 4 lights per slot are 4.1 % faster than 3 at 64 and at 16 lights, 3 are 2.7 %
+//    faster at 9 lights (9 = 4+4+1: the odd light takes the guarded partial-slot path); 5, 6, 8 are slower than 4.
+//    The launcher picks 3 or 4 from the light count (pick_chunk).
+template <int CW, int LANES, int MAXNREG, int CHUNK = 3>
 struct TileShape {
   static constexpr int kCW = CW;
   static constexpr int kLanes = LANES;
   static constexpr int kTile = 32 * CW * LANES;      // texels per tile
   static constexpr int kConsumers = 32 * CW;         // consumer threads
   static constexpr int kThreads = 32 * (CW + 1);     // + the producer warp
-  static constexpr int kSlotBytes = 9 * kTile * 4;   // one ring slot: 9 plane segments
+  static constexpr int kChunk = CHUNK;               // lights per ring slot
+  static constexpr int kSlotPlanes = 3 * CHUNK > 9 ? 3 * CHUNK : 9;
+  static constexpr int kSlotBytes = kSlotPlanes * kTile * 4;   // one ring slot: 9 plane segments (12 with 4-light slots)
   static constexpr int kMaxReg = MAXNREG;
 };
 #ifndef SV_CONSUMER_WARPS
@@ -73,9 +80,9 @@ struct TileShape {
 #ifndef SV_PACKED_DEFAULT
 #define SV_PACKED_DEFAULT 0
 #endif
-typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG> ScalarShape;
-typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG> PackedShape;
-constexpr int kChunkLights = 3;        // tile_kernel: lights per ring slot
+typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 3> ScalarShape;
+typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 4> ScalarShape4;
+typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG, 3> PackedShape;
 // SV_STASH: park the values only the epilogue needs (raw texel, gamma derivatives, normal reconstruction:
 // 29 floats per texel) in shared memory while the light loop runs, instead of in registers: the compiler
 // then stops rematerialising per-texel constants inside the loop.  Measured (profiles/r01_variants.txt):
@@ -702,8 +709,8 @@ __device__ __forceinline__ void mbar_wait_uniform(unsigned long long* bar, unsig
 
 // Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
 template <int MODE>
-__host__ __device__ __forceinline__ int chunks_per_tile(int n_lights) {
-  return 1 + (n_lights + kChunkLights - 1) / kChunkLights + (MODE == kModeL2Adam ? 2 : 0);
+__host__ __device__ __forceinline__ int chunks_per_tile(int n_lights, int chunk) {
+  return 1 + (n_lights + chunk - 1) / chunk + (MODE == kModeL2Adam ? 2 : 0);
 }
 
 template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
@@ -790,15 +797,15 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     Grads<float> g;
     grads_zero(g);
 
-    // ---- lights, 3 per ring slot ----
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
-      float in[kChunkLights][3];
+    // ---- lights, SH::kChunk per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
+      float in[SH::kChunk][3];
       mbar_wait(&full[slot], phase);
       const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
-      if (i0 + kChunkLights <= N) {
+      if (i0 + SH::kChunk <= N) {
         // full chunk: no per-light guards, so the three independent lights can be interleaved
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]);
         }
@@ -806,24 +813,24 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         advance();
 #if SV_STREAM_ONLY
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
+        for (int j = 0; j < SH::kChunk; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
 #else
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
           float o3[3];
           shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
         }
 #endif
       } else {
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
         }
         release(slot);
         advance();
 #pragma unroll
-        for (int j = 0; j < kChunkLights - 1; ++j) {       // a partial chunk holds at most kChunkLights-1 lights
+        for (int j = 0; j < SH::kChunk - 1; ++j) {       // a partial chunk holds at most SH::kChunk-1 lights
           if (i0 + j < N) {
             float o3[3];
             shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
@@ -1069,34 +1076,34 @@ __device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __
     Grads<T> g;
     grads_zero(g);
 
-    // ---- lights, 3 per ring slot ----
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
-      T in[kChunkLights][3];
+    // ---- lights, SH::kChunk per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
+      T in[SH::kChunk][3];
       mbar_wait(&full[slot], phase);
       const unsigned char* s = ring + size_t(slot) * SH::kSlotBytes;
-      if (i0 + kChunkLights <= N) {
+      if (i0 + SH::kChunk <= N) {
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = IoLoad2<TGT>::at(s, j * 3 + c, SH::kTile, tid);
         }
         release(slot);
         advance();
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
           T o3[3];
           shade_light<T, LM, COLOC, WANT_POW>(tx, load_geom2<COLOC>(s_geo, i0 + j), in[j], o3, g);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad2<TGT>::at(s, j * 3 + c, SH::kTile, tid) : T(0.f);
         }
         release(slot);
         advance();
 #pragma unroll
-        for (int j = 0; j < kChunkLights - 1; ++j) {
+        for (int j = 0; j < SH::kChunk - 1; ++j) {
           if (i0 + j < N) {
             T o3[3];
             shade_light<T, LM, COLOC, WANT_POW>(tx, load_geom2<COLOC>(s_geo, i0 + j), in[j], o3, g);
@@ -1230,8 +1237,8 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
     const float* tex_src = P.tex;
     if (MODE == kModeL2Grad && P.push_pull) tex_src = P.push_tex[p0 / P.push_chunk];
     fill(tex_src, 4, 9);
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
-      const int nl = min(kChunkLights, N - i0);
+    for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
+      const int nl = min(SH::kChunk, N - i0);
       fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
     }
     if (MODE == kModeL2Adam) {
@@ -1402,14 +1409,14 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
     Grads<float> g;
     grads_zero(g);
 
-    // ---- lights, 3 per ring slot ----
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
-      float in[kChunkLights][3];
+    // ---- lights, SH::kChunk per ring slot ----
+    for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
+      float in[SH::kChunk][3];
       mbar_wait(&B.full[slot], phase);
       const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes + off_e);
-      if (i0 + kChunkLights <= N) {
+      if (i0 + SH::kChunk <= N) {
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * kBoxW]);
         }
@@ -1417,24 +1424,24 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
         advance();
 #if SV_STREAM_ONLY
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
+        for (int j = 0; j < SH::kChunk; ++j) g.loss += in[j][0] + in[j][1] + in[j][2];
 #else
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
           float o3[3];
           shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
         }
 #endif
       } else {
 #pragma unroll
-        for (int j = 0; j < kChunkLights; ++j) {
+        for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kBoxW]) : 0.f;
         }
         release(slot);
         advance();
 #pragma unroll
-        for (int j = 0; j < kChunkLights - 1; ++j) {       // a partial chunk holds at most kChunkLights-1 lights
+        for (int j = 0; j < SH::kChunk - 1; ++j) {       // a partial chunk holds at most SH::kChunk-1 lights
           if (i0 + j < N) {
             float o3[3];
             shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
@@ -1530,7 +1537,7 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
   typedef typename IoLoad<TGT>::elem elem;
   const int N = P.n_lights, S = P.slots;
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
-  const unsigned CL = unsigned((N + kChunkLights - 1) / kChunkLights);        // light chunks per tile
+  const unsigned CL = unsigned((N + SH::kChunk - 1) / SH::kChunk);        // light chunks per tile
   const unsigned C = CL + (MODE == kModeL2Adam ? 2u : 0u);                     // ring chunks per tile
   const unsigned M = unsigned((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const unsigned total = M * unsigned(P.epochs);
@@ -1596,7 +1603,7 @@ __device__ __forceinline__ void tile_producer_ts(const Params& P, unsigned char*
 #pragma unroll
       for (int q = 0; q < kBoxes; ++q) tma_load_box(&P.tm_tex, dst + q * kBoxF, x0 + q * kBoxW, 0, bar);
     }
-    for (int i0 = 0; i0 < N; i0 += kChunkLights) {
+    for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
       wait_serving(&B.empty[slot], phase ^ 1);
       if (leader) {
         const unsigned dst = smem_u32(ring) + slot * unsigned(SH::kSlotBytes);
@@ -1922,7 +1929,7 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   const size_t budget = size_t(d.smem_optin + 1024) / ctas_per_sm - 1024 - static_smem;
   int slots = env_int("SVBRDF_B200_SLOTS", 0);
   if (slots <= 0) slots = int((budget - fixed) / SH::kSlotBytes);
-  const int need = chunks_per_tile<MODE>(P.n_lights);
+  const int need = chunks_per_tile<MODE>(P.n_lights, SH::kChunk);
   if (slots > 2 * need) slots = 2 * need;                               // two whole tiles in flight is plenty
   if (slots > 64) slots = 64;
   if (slots < 2) return launch_texel<MODE, WANT_POW, TGT>(P, st);
@@ -2015,7 +2022,7 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
   if (size_t(d.smem_optin) < fixed + static_smem + 3 * size_t(SH::kSlotBytes)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
   int slots = env_int("SVBRDF_B200_SLOTS", 0);
   if (slots <= 0) slots = int((size_t(d.smem_optin) - static_smem - fixed) / SH::kSlotBytes);
-  const int need = chunks_per_tile<MODE>(P.n_lights) - 1;              // the texture chunk is not in the ring
+  const int need = chunks_per_tile<MODE>(P.n_lights, SH::kChunk) - 1;              // the texture chunk is not in the ring
   if (slots > 2 * need) slots = 2 * need;
   if (slots > 64) slots = 64;
   if (slots < 3) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
@@ -2054,6 +2061,16 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
   return int(cudaGetLastError());
 }
 
+// Lights per ring slot (TileShape CHUNK) for a light count: whole slots are shaded unguarded and interleaved, the lights
+// left over in a partial slot one by one behind guards — so fewest left-over lights first, then the larger slot.
+// SVBRDF_B200_CHUNK=3|4 overrides (development).
+static int pick_chunk(int n_lights) {
+  const int forced = env_int("SVBRDF_B200_CHUNK", 0);
+  if (forced == 3 || forced == 4) return forced;
+  if (n_lights < 4) return 3;
+  return (n_lights % 4) <= (n_lights % 3) ? 4 : 3;
+}
+
 template <int MODE, bool WANT_POW, int TGT>
 static int launch_tile(Params P, cudaStream_t st) {
   if (env_int("SVBRDF_B200_FORCE_LDG", 0) || !tma_ok<TGT>(P)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
@@ -2065,6 +2082,7 @@ static int launch_tile(Params P, cudaStream_t st) {
 #if SV_ENABLE_PACKED
   if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
 #endif
+  if (pick_chunk(P.n_lights) == 4) return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape4>(P, st);
   return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 }
 
