@@ -9,12 +9,12 @@
 //
 // Two kernels implement that pass:
 //
-//  * tile_kernel  (the hot path) — persistent, warp-specialised.  Each CTA walks over 256-texel
-//    tiles.  A producer warp streams every byte the tile needs (texture planes, 3 lights of
+//  * tile_kernel  (the hot path) — persistent, warp-specialised.  Each CTA walks over 480-texel
+//    tiles.  A producer warp streams every byte the tile needs (texture planes, 3 or 4 lights of
 //    targets per chunk, Adam m and v) from HBM into a shared-memory ring with 1-D TMA bulk copies
-//    (cp.async.bulk ... mbarrier::complete_tx); eight consumer warps wait on the slot's mbarrier,
+//    (cp.async.bulk ... mbarrier::complete_tx); 15 consumer warps wait on the slot's mbarrier,
 //    pull their texel's values with conflict-free LDS, release the slot and compute.  The ring
-//    keeps up to kSlots x 9 KB per CTA in flight without costing the consumers a single register,
+//    keeps 7-9 slots of 17-23 KB per CTA in flight without costing the consumers a single register,
 //    which is what the first version of this kernel (plain LDG with a 2-light register prefetch)
 //    could not do: ncu showed 6.8 warps per issue slot stalled on long-scoreboard at 24 %
 //    occupancy (profiles/r01_v1_ldg_*.txt).  Results leave through coalesced STG.
@@ -707,7 +707,7 @@ __device__ __forceinline__ void mbar_wait_uniform(unsigned long long* bar, unsig
   }
 }
 
-// Chunk stream of one tile:  [tex] [lights 0..2] [lights 3..5] ... ([m] [v] in the fused mode).
+// Chunk stream of one tile:  [tex] [lights 0..L-1] [lights L..2L-1] ... ([m] [v] in the fused mode), L = SH::kChunk.
 template <int MODE>
 __host__ __device__ __forceinline__ int chunks_per_tile(int n_lights, int chunk) {
   return 1 + (n_lights + chunk - 1) / chunk + (MODE == kModeL2Adam ? 2 : 0);
