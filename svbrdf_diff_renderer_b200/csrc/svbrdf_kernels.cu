@@ -77,6 +77,9 @@ struct TileShape {
 #ifndef SV_ENABLE_PACKED
 #define SV_ENABLE_PACKED 1
 #endif
+#ifndef SV_ENABLE_TS
+#define SV_ENABLE_TS 1                 // the store-back kernel is written for 480-texel tiles: 0 for builds with other SV_CONSUMER_WARPS
+#endif
 #ifndef SV_PACKED_DEFAULT
 #define SV_PACKED_DEFAULT 0
 #endif
@@ -2077,8 +2080,10 @@ static int launch_tile(Params P, cudaStream_t st) {
   const bool out_ok = MODE == kModeL2Adam || (reinterpret_cast<uintptr_t>(P.out) & 15) == 0;
   // opt-in (SVBRDF_B200_TSTORE=1): measured 72.3 vs 71.2 us per epoch at 1024^2 x 9 and 1320 vs 1232 us at 2048^2 x 64 against the
   // per-thread-store kernel below, although it executes 8 % fewer instructions
+#if SV_ENABLE_TS
   if (P.push_world == 0 && P.tile_rotate == 0 && out_ok && !env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT) && env_int("SVBRDF_B200_TSTORE", 0))
     return launch_tile_ts<MODE, WANT_POW, TGT, ScalarShape>(P, st);
+#endif
 #if SV_ENABLE_PACKED
   if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
 #endif
