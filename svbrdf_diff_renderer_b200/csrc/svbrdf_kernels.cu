@@ -77,6 +77,9 @@ struct TileShape {
 #ifndef SV_ENABLE_PACKED
 #define SV_ENABLE_PACKED 1
 #endif
+#ifndef SV_PROBE_AHEAD
+#define SV_PROBE_AHEAD 0               // measured slower (profiles/r01_s3_variants_probe_ahead.txt): off
+#endif
 #ifndef SV_ENABLE_TS
 #define SV_ENABLE_TS 1                 // the store-back kernel is written for 480-texel tiles: 0 for builds with other SV_CONSUMER_WARPS
 #endif
@@ -673,6 +676,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (acquire): true if the phase with this parity has completed.
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -730,7 +747,18 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 
   unsigned it = 0;        // running chunk index of this CTA
   unsigned slot = 0, phase = 0;
+  // SV_PROBE_AHEAD (off): right after a slot is handed back, the NEXT slot's `full` barrier is probed without blocking, so
+  // the common case (data already there) starts the next chunk without the try_wait round trip.  The ncu source view at
+  // 4096^2 x 64 attributes 9 % of the warp samples to the branch on the try_wait result and its convergence bookkeeping,
+  // yet hiding it is 1.8 % SLOWER at 64 lights and 2.1 % at 9: those samples are slack, not the critical path.
+  bool ready = false;
+#if SV_PROBE_AHEAD
+  auto advance = [&]() { ++it; if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } ready = mbar_test(&full[slot], phase); };
+  auto wait_full = [&]() { if (!ready) mbar_wait(&full[slot], phase); };
+#else
   auto advance = [&]() { ++it; if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
+  auto wait_full = [&]() { mbar_wait(&full[slot], phase); };
+#endif
   auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
 
   // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
@@ -752,7 +780,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     // ---- texel prologue ----
     float raw[9], t[9];
     bool outer[9];
-    mbar_wait(&full[slot], phase);
+    wait_full();
     {
       const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
@@ -803,7 +831,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     // ---- lights, SH::kChunk per ring slot ----
     for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
       float in[SH::kChunk][3];
-      mbar_wait(&full[slot], phase);
+      wait_full();
       const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
       if (i0 + SH::kChunk <= N) {
         // full chunk: no per-light guards, so the three independent lights can be interleaved
@@ -869,7 +897,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #endif
     if (MODE == kModeL2Adam) {
       float mk[9], vk[9];
-      mbar_wait(&full[slot], phase);
+      wait_full();
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
@@ -877,7 +905,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       }
       release(slot);
       advance();
-      mbar_wait(&full[slot], phase);
+      wait_full();
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
