@@ -208,6 +208,9 @@ constexpr int kRowsPerEpoch = 4096;     // workspace rows ([loss, gpow x3]) per 
 #ifndef SV_U8_MAGIC
 #define SV_U8_MAGIC 0
 #endif
+#ifndef SV_U8_I2FP
+#define SV_U8_I2FP 1                   // measured (profiles/r01_s3_variants_u8_i2fp.txt): 1371 -> 1283 us at 2048^2 x 64, 77.7 -> 74.8 us at 1024^2 x 9
+#endif
 template <int TGT>
 struct IoLoad;
 template <>
@@ -227,6 +230,11 @@ struct IoLoad<SVBRDF_TARGET_U8> {
     // integer -> float without I2F (quarter-rate conversion pipe): 2^23 + b as a bit pattern, minus 2^23 (exact).
     // Measured: 77.4 vs 74.8 us per epoch at 1024^2 x 9 with uint8 targets — the extra issue slot costs more; off.
     const float b = __uint_as_float(0x4B000000u | unsigned(x)) - 8388608.0f;
+#elif SV_U8_I2FP
+    // 32-bit conversion: I2FP.F32.U32 runs on the ALU pipe, the 16-bit form the compiler picks for a byte (I2F.U16) on the
+    // quarter-rate conversion (XU) pipe next to the 10 MUFU operations of the light body
+    float b;
+    asm("cvt.rn.f32.u32 %0, %1;" : "=f"(b) : "r"(unsigned(x)));
 #else
     const float b = float(x);
 #endif
