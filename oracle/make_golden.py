@@ -138,9 +138,48 @@ def make_stats_256():
     print(f"config1 stats: loss {out['loss_f32'][0]:.6g} -> {out['loss_f32'][-1]:.6g}   ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def make_stats_1024():
+    """Config 2 of BASELINE.json (1024^2 x 9, 20 epochs, run.py:56): loss curves, per-channel sums and three 8-row
+    strips of the final maps (top, middle, bottom), fp32 and fp64, from the unmodified reference."""
+    res, n = 1024, 9
+    cl = synth.calibration(n, True)
+    tex_gt, tex0 = synth.random_textures(res, 1), synth.random_textures(res, 2)
+    r32, _ = _renderer(res, n, cl)
+    with th.no_grad():
+        target = r32.eval(tex_gt)
+    out = {}
+    strips = ((0, 8), (508, 516), (1016, 1024))
+    for tag, dbl in (("f32", False), ("f64", True)):
+        maps, loss, g0, _, _ = _run_optim(res, n, cl, tex0, target, 20, 0.01, False, dbl)
+        out[f"loss_{tag}"] = loss
+        out[f"grad0_chan_sum_{tag}"] = g0.double().sum((0, 2, 3)).numpy()
+        out[f"grad0_chan_abs_{tag}"] = g0.double().abs().sum((0, 2, 3)).numpy()
+        out[f"maps_chan_sum_{tag}"] = maps.double().sum((0, 2, 3)).numpy()
+        out[f"maps_chan_sq_{tag}"] = (maps.double() ** 2).sum((0, 2, 3)).numpy()
+        out[f"maps_strips_{tag}"] = np.concatenate([maps[:, :, a:b, :].numpy() for a, b in strips], 2)
+        out[f"grad0_strips_{tag}"] = np.concatenate([g0[:, :, a:b, :].numpy() for a, b in strips], 2)
+    out["target_chan_sum"] = target.double().sum((0, 2, 3)).numpy()
+    out["target_sq_sum"] = float((target.double() ** 2).sum())
+    path = os.path.join(OUT, "config2_1024x9_stats.npz")
+    np.savez_compressed(path, res=res, n=n, seed_gt=1, seed_start=2, strips=np.array(strips), **out)
+    print(f"config2 stats: loss {out['loss_f32'][0]:.6g} -> {out['loss_f32'][-1]:.6g}   ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
+    import sys
+    only = set(sys.argv[1:])
     os.makedirs(OUT, exist_ok=True)
     th.set_num_threads(os.cpu_count() or 1)
+    if only:
+        # python -m oracle.make_golden config2 nonpow2   (regenerate a subset; the default regenerates the round-1 set)
+        if "nonpow2" in only:
+            # non-power-of-two resolutions through the TMA kernel (40^2, 48^2 texels are multiples of 4): (j + 0.5)/R is not
+            # exactly (j + 0.5) * (1/R) there (microfacet.py:16-19)
+            make_case("coloc_40x9", 40, 9, True, synth.random_textures(40, 31), synth.random_textures(40, 32))
+            make_case("offaxis_48x9", 48, 9, False, synth.random_textures(48, 33), synth.random_textures(48, 34), epochs=10)
+        if "config2" in only:
+            make_stats_1024()
+        return
     make_case("coloc_32x9", 32, 9, True, synth.random_textures(32, 1), synth.random_textures(32, 2))
     make_case("offaxis_32x9", 32, 9, False, synth.random_textures(32, 1), synth.random_textures(32, 2))
     make_case("edges_32x9", 32, 9, True, synth.random_textures(32, 1), synth.edge_case_textures(32))

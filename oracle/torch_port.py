@@ -163,10 +163,14 @@ def image_grad(scene, tex, grad_img, power=None):
     return tex.grad.detach(), (pw.grad.detach() if pw is not None else None), img.detach()
 
 
-def optimise(scene, tex0, target, epochs, lr, power=None, optim_light=False, on_epoch=None):
+def optimise(scene, tex0, target, epochs, lr, power=None, optim_light=False, on_epoch=None, loss_scale=None):
     """The loop body of ``SvbrdfOptim.optim`` (svbrdf.py:48-71) without tqdm and dumps.
 
     Returns (final unclamped textures, list of per-epoch losses, final power).
+
+    ``loss_scale`` (big-config oracle only): when ``scene`` is a row band of a larger image, the
+    band's MSE mean is rescaled by rows_in_band/rows_in_image so the gradient — and with it Adam's eps-dependent
+    step — is the full image's (texels are independent; the loss returned is then the band's SHARE of the full loss).
     """
     tex = tex0.detach().clone().to(scene.dtype).requires_grad_(True)
     target = target.to(scene.dtype)
@@ -182,6 +186,8 @@ def optimise(scene, tex0, target, epochs, lr, power=None, optim_light=False, on_
             scene.set_power(pw)
         img = shade(scene, tex.clamp(-1, 1))
         loss = l2_loss(img, target)
+        if loss_scale is not None:
+            loss = loss * loss_scale
         losses.append(loss.item())
         opt.zero_grad()
         loss.backward()

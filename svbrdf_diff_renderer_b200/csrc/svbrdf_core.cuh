@@ -237,6 +237,7 @@ struct Texel {
   T omsp[3];         // pw_c * (1 - s_c)                     (Fresnel: F_c*pw_c = sp + omsp*sphg)
   T Fp[3];           // pw_c * F_c for a co-located pair (constant per texel)
   T a2, k, omk;      // alpha^2, k = alpha/2 + eps, 1 - k  (alpha = rough^2), microfacet.py:30,51,106
+  T a2q, a2m1x2;     // a2/4 and 2 (a2 - 1): per-texel constants of the co-located light body
 };
 
 template <typename T>
@@ -255,7 +256,8 @@ template <typename T>
 struct Grads {       // accumulated over lights (without the constant image-gradient factor)
   T kdp[3];          // dL/d kdp_c
   T sF[3];           // sum of gfp_c * Q * (1 - sphg)   (co-located: sum of gfp_c * Q; (1-sphg) applied in the epilogue)
-  T a2, k;
+  T a2, k;           // general lights: dL/da2, dL/dk.  Co-located lights: SA = sum T u c^2 / 2 and SK = sum T (1-c)/gv (see shade_light_coloc)
+  T sT;              // co-located lights: sum of T = gQ * Q (dL/da2 = sT/a2 - 2 SA)
   T n[3];
   T pw[3];           // sum of gfp_c * fp_c = pw_c * dL/dpw_c (only when requested)
   T loss;            // sum of squared differences (L2 modes)
@@ -275,14 +277,19 @@ SV_HD void texel_position(int row, int col, int res, float size, T& px, T& py) {
   py = T(-fy);
 }
 
-// Same with the division replaced by a multiplication with 1/res (what torch's CUDA division by a
-// scalar does as well): identical for power-of-two resolutions, within 1 ulp of the position otherwise.
+// The same value without the division instruction sequence: q = a/res correctly rounded from the correctly rounded
+// reciprocal r = RN(1/res) by one residual correction (Markstein): q0 = RN(a r), rem = a - q0 res (exact in an FMA),
+// q = RN(q0 + rem r).  Bit-identical to texel_position for every resolution (tests/test_host_logic.py checks all
+// (index, res) pairs up to 4096 and a set of larger ones), power of two or not.
 template <typename T>
-SV_HD void texel_position_rcp(int row, int col, float inv_res, float size, T& px, T& py) {
-  const float fx = ((float(col) + 0.5f) * inv_res - 0.5f) * size;
-  const float fy = ((float(row) + 0.5f) * inv_res - 0.5f) * size;
-  px = T(fx);
-  py = T(-fy);
+SV_HD void texel_position_rcp(int row, int col, float res_f, float inv_res, float size, T& px, T& py) {
+  typedef Fm<float> S;
+  const float ax = float(col) + 0.5f, ay = float(row) + 0.5f;
+  float qx = S::mul(ax, inv_res), qy = S::mul(ay, inv_res);
+  qx = S::fma(S::fma(-qx, res_f, ax), inv_res, qx);
+  qy = S::fma(S::fma(-qy, res_f, ay), inv_res, qy);
+  px = T((qx - 0.5f) * size);
+  py = T(-((qy - 0.5f) * size));
 }
 
 // Prologue: 9 channels -> material parameters.  `t` must already be clamped to [-1,1]
@@ -312,6 +319,8 @@ SV_HD void texel_prologue(const T t[9], const T pw[3], Texel<T>& tx, TexelAux<T>
   tx.a2 = ax.alpha * ax.alpha;
   tx.k = ax.alpha * T(0.5) + T(kEps);
   tx.omk = T(1) - tx.k;
+  tx.a2q = tx.a2 * T(0.25);
+  tx.a2m1x2 = (tx.a2 - T(1)) * T(2);
 
   ax.in3 = Fm<T>::mand(Fm<T>::ge(t[3], T(-1)), Fm<T>::le(t[3], T(1)));
   ax.in4 = Fm<T>::mand(Fm<T>::ge(t[4], T(-1)), Fm<T>::le(t[4], T(1)));
@@ -331,7 +340,7 @@ SV_HD void texel_prologue(const T t[9], const T pw[3], Texel<T>& tx, TexelAux<T>
 template <typename T>
 SV_HD void grads_zero(Grads<T>& g) {
   for (int c = 0; c < 3; ++c) g.kdp[c] = g.sF[c] = g.n[c] = g.pw[c] = T(0);
-  g.a2 = g.k = g.loss = g.loss_g = T(0);
+  g.a2 = g.k = g.sT = g.loss = g.loss_g = T(0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -511,6 +520,201 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
   }
 }
 
+// SV_COLOC_V2: the co-located light body rewritten for fewer issued instructions (the kernel is issue-bound, DESIGN.md
+// section 3.1): 109 -> ~97 SASS instructions per pixel.light.  Same formulas, different evaluation order:
+//   * 1 - c^2 is formed as the cross-product identity (V.V - (n.V)^2)/V.V with ONE rounding of the difference (FMA): the
+//     GGX denominator den = c^2 a2 + (1 - c^2) no longer cancels against the error of the MUFU.RSQ normalisation, so the
+//     Newton step on rsqrt (4 instructions) is gone — and den is more accurate than the reference's own fp32 `1 - c*c`;
+//   * q/4 = c^2 + eps/4 instead of q = 4 c^2 + eps (exact scaling by a power of two): 4/q comes out of the MUFU.RCP
+//     for free where the derivative needs it, the 1/4 is folded into the per-texel constant a2/4;
+//   * QR = Q/c is formed on the way to Q and reused for the 2Q/c term of dQ/dc;
+//   * the material gradients are accumulated as sum T (T = gQ Q), sum T u c^2 / 2 and sum T (1-c)/gv; the per-texel
+//     factors 1/a2, -2 are applied once in the epilogue;
+//   * the accumulators take the image gradient gI_c directly (fma(gI, w, .), fma(gI, w Q, .)) instead of dL/dfp_c.
+#ifndef SV_COLOC_V2
+#define SV_COLOC_V2 1
+#endif
+
+// SV_PRED_ACC (device, float): the clamp mask of the image gradient predicates the accumulating FMAs instead of
+// selecting a zero first (one FSEL per channel less).
+#ifndef SV_PRED_ACC
+#define SV_PRED_ACC 0
+#endif
+
+template <typename T, int MODE, bool WANT_POW>
+SV_HD void channels_coloc(const Texel<T>& tx, T w, T Q, const T io[3], T out[3], Grads<T>& g, T& B, T& gw, const T* tgt, T l2w) {
+  typedef Fm<T> F;
+  T fp[3], I[3], Icl[3];
+  for (int c = 0; c < 3; ++c) {
+    fp[c] = F::fma(Q, tx.Fp[c], tx.kdp[c]);                   // pw_c f_c, microfacet.py:102-109
+    I[c] = fp[c] * w;                                         // microfacet.py:117
+    Icl[c] = F::min(F::max(I[c], T(kEps)), T(1));             // microfacet.py:120
+  }
+  if (MODE == kRender) {
+    for (int c = 0; c < 3; ++c) out[c] = F::mul(F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma - 1.0)), Icl[c]);
+    return;
+  }
+  const T wQ = w * Q;
+  B = T(0);
+  gw = T(0);
+  for (int c = 0; c < 3; ++c) {
+    const T slope = F::ex2(F::lg2(Icl[c]) * T(1.0 / kGamma - 1.0));   // Icl^(1/gamma - 1); 1/gamma applied in the epilogue
+    T up;
+    if (MODE == kL2) {
+      const T diff = F::sub(F::mul(slope, Icl[c]), io[c]);   // Icl^(1/gamma) - target, rounded like the render
+      g.loss = F::fma(diff, diff, g.loss);
+      up = diff;
+    } else if (MODE == kVjpL2) {
+      const T diff = F::sub(F::mul(slope, Icl[c]), tgt[c]);
+      g.loss = F::fma(diff, diff, g.loss);
+      up = F::fma(diff, l2w, io[c]);
+    } else {
+      up = io[c];
+    }
+    const T gI = F::sel(F::eq(I[c], Icl[c]), up * slope, T(0));   // clamp masks are inclusive
+    g.kdp[c] = F::fma(gI, w, g.kdp[c]);
+    g.sF[c] = F::fma(gI, wQ, g.sF[c]);
+    B = F::fma(gI, tx.Fp[c], B);
+    gw = F::fma(gI, fp[c], gw);
+    if (WANT_POW) g.pw[c] = F::fma(gI, I[c], g.pw[c]);       // gfp_c fp_c = gI_c I_c
+  }
+}
+
+#if SV_PAIR_RG && defined(__CUDA_ARCH__)
+// float instantiation on the device: the R and G chains share packed FP32x2 instructions, B stays scalar
+template <int MODE, bool WANT_POW>
+SV_D void channels_coloc_rg(const Texel<float>& tx, float w, float Q, const float io[3], Grads<float>& g, float& B, float& gw) {
+  typedef Fm<float> S;
+  typedef Fm<V2> F;
+  const V2 QQ(Q), ww(w);
+  const V2 FpRG(tx.Fp[0], tx.Fp[1]);
+  const V2 fpRG = F::fma(QQ, FpRG, V2(tx.kdp[0], tx.kdp[1]));
+  const float fpB = S::fma(Q, tx.Fp[2], tx.kdp[2]);
+  const V2 IRG = fpRG * ww;
+  const float IB = fpB * w;
+  const V2 IclRG(S::min(S::max(IRG.x, float(kEps)), 1.f), S::min(S::max(IRG.y, float(kEps)), 1.f));
+  const float IclB = S::min(S::max(IB, float(kEps)), 1.f);
+  const V2 es = V2(S::lg2(IclRG.x), S::lg2(IclRG.y)) * V2(1.0 / kGamma - 1.0);
+  const V2 slopeRG(S::ex2(es.x), S::ex2(es.y));
+  const float slopeB = S::ex2(S::lg2(IclB) * float(1.0 / kGamma - 1.0));
+  V2 upRG;
+  float upB;
+  if (MODE == kL2) {
+    // two scalar FMULs, not one FMUL2: ptxas would fuse the packed product with the subtraction into an FFMA2 and the L2
+    // forward would no longer reproduce the render bit for bit
+    const V2 oRG(S::mul(slopeRG.x, IclRG.x), S::mul(slopeRG.y, IclRG.y));
+    const float oB = S::mul(slopeB, IclB);
+    upRG = oRG - V2(io[0], io[1]);
+    upB = oB - io[2];
+    const V2 l2 = F::fma(upRG, upRG, V2(g.loss, g.loss_g));
+    g.loss_g = l2.y;
+    g.loss = S::fma(upB, upB, l2.x);
+  } else {
+    upRG = V2(io[0], io[1]);
+    upB = io[2];
+  }
+  const V2 t = upRG * slopeRG;
+  const float tB = upB * slopeB;
+  const float wQ = w * Q;
+#if SV_PRED_ACC
+  {
+    // channel R selects (it initialises B and gw), G and B predicate their accumulations on the clamp mask
+    const float gIR = (IRG.x == IclRG.x) ? t.x : 0.f;
+    g.kdp[0] = S::fma(gIR, w, g.kdp[0]);
+    g.sF[0] = S::fma(gIR, wQ, g.sF[0]);
+    B = gIR * tx.Fp[0];
+    gw = gIR * fpRG.x;
+    if (WANT_POW) g.pw[0] = S::fma(gIR, IRG.x, g.pw[0]);
+    asm("{\n .reg .pred p;\n setp.eq.f32 p, %4, %5;\n @p fma.rn.f32 %0, %6, %7, %0;\n @p fma.rn.f32 %1, %6, %8, %1;\n"
+        " @p fma.rn.f32 %2, %6, %9, %2;\n @p fma.rn.f32 %3, %6, %10, %3;\n}"
+        : "+f"(g.kdp[1]), "+f"(g.sF[1]), "+f"(B), "+f"(gw)
+        : "f"(IRG.y), "f"(IclRG.y), "f"(t.y), "f"(w), "f"(wQ), "f"(tx.Fp[1]), "f"(fpRG.y));
+    asm("{\n .reg .pred p;\n setp.eq.f32 p, %4, %5;\n @p fma.rn.f32 %0, %6, %7, %0;\n @p fma.rn.f32 %1, %6, %8, %1;\n"
+        " @p fma.rn.f32 %2, %6, %9, %2;\n @p fma.rn.f32 %3, %6, %10, %3;\n}"
+        : "+f"(g.kdp[2]), "+f"(g.sF[2]), "+f"(B), "+f"(gw)
+        : "f"(IB), "f"(IclB), "f"(tB), "f"(w), "f"(wQ), "f"(tx.Fp[2]), "f"(fpB));
+    if (WANT_POW) {
+      g.pw[1] = S::fma((IRG.y == IclRG.y) ? t.y : 0.f, IRG.y, g.pw[1]);
+      g.pw[2] = S::fma((IB == IclB) ? tB : 0.f, IB, g.pw[2]);
+    }
+  }
+#else
+  const V2 gIRG(IRG.x == IclRG.x ? t.x : 0.f, IRG.y == IclRG.y ? t.y : 0.f);
+  const float gIB = (IB == IclB) ? tB : 0.f;
+  {
+    const V2 k2 = F::fma(gIRG, ww, V2(g.kdp[0], g.kdp[1]));
+    g.kdp[0] = k2.x; g.kdp[1] = k2.y;
+    g.kdp[2] = S::fma(gIB, w, g.kdp[2]);
+    const V2 s2 = F::fma(gIRG, V2(wQ), V2(g.sF[0], g.sF[1]));
+    g.sF[0] = s2.x; g.sF[1] = s2.y;
+    g.sF[2] = S::fma(gIB, wQ, g.sF[2]);
+  }
+  const V2 a = gIRG * fpRG, b = gIRG * FpRG;
+  gw = S::fma(gIB, fpB, a.x + a.y);
+  B = S::fma(gIB, tx.Fp[2], b.x + b.y);
+  if (WANT_POW) {
+    const V2 c = gIRG * IRG;
+    g.pw[0] += c.x; g.pw[1] += c.y;
+    g.pw[2] = S::fma(gIB, IB, g.pw[2]);
+  }
+#endif
+}
+#endif
+
+#if SV_COLOC_V2
+template <typename T, int MODE, bool WANT_POW>
+SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T io[3], T out[3], Grads<T>& g,
+                             const T* tgt = nullptr, T l2w = T(0)) {
+  typedef Fm<T> F;
+  const T Vx = lg.cx - tx.px, Vy = lg.cy - tx.py, Vz = lg.cz;
+  const T vv = F::fma(Vx, Vx, F::fma(Vy, Vy, lg.cz2));        // |V|^2, microfacet.py:60-62
+  const T rv = F::rsqrt(vv);
+  const T nV = F::fma(tx.n[0], Vx, F::fma(tx.n[1], Vy, tx.n[2] * Vz));
+  const T c = F::max(nV * rv, T(0));                          // n.v = n.l = n.h, clamp(min=0) (microfacet.py:96-98)
+  const T inv_d2 = rv * rv;
+  const T w = c * inv_d2;                                     // n.l / d^2
+  const T c2 = c * c;
+  const T s2 = F::fma(-nV, nV, vv) * inv_d2;                  // 1 - (n.v)^2 without cancellation error (|n| = 1)
+  const T den = F::fma(c2, tx.a2, s2);                        // c2 a2 + 1 - c2, microfacet.py:30
+  const T pden = T(kPi) * den;
+  const T Dd = F::fma(pden, den, T(kEps));                    // microfacet.py:31
+  const T gv = F::fma(c, tx.omk, tx.k);                       // microfacet.py:49
+  const T q4 = c2 + T(0.25 * kEps);                           // (4 n.v n.l + eps)/4, microfacet.py:109
+  const T rDd = F::rcp(Dd), rgv = F::rcp(gv), rq4 = F::rcp(q4);
+  const T Rc = c * rDd * (rgv * rgv) * rq4;                   // 4 Q / (a2 c)
+  const T QR = Rc * tx.a2q;                                   // Q / c
+  const T Q = QR * c;                                         // D G / q
+  T B, gw;
+#if SV_PAIR_RG && defined(__CUDA_ARCH__)
+  if (sizeof(T) == 4 && (MODE == kVjp || MODE == kL2)) {
+    channels_coloc_rg<MODE, WANT_POW>(*reinterpret_cast<const Texel<float>*>(&tx), *reinterpret_cast<const float*>(&w),
+                                      *reinterpret_cast<const float*>(&Q), reinterpret_cast<const float*>(io),
+                                      *reinterpret_cast<Grads<float>*>(&g), *reinterpret_cast<float*>(&B), *reinterpret_cast<float*>(&gw));
+  } else
+#endif
+  {
+    channels_coloc<T, MODE, WANT_POW>(tx, w, Q, io, out, g, B, gw, tgt, l2w);
+  }
+  if (MODE == kRender) return;
+
+  const T gQ = w * B;                                         // dL/dQ = sum_c dL/dfp_c Fp_c
+  const T Tq = gQ * Q;
+  g.sT += Tq;
+  const T E = Tq * (rDd * pden);                              // T u/2, u = (dDd/dden)/Dd
+  g.a2 = F::fma(E, c2, g.a2);                                 // SA
+  const T Ggv = Tq * rgv;
+  g.k = F::fma(Ggv, T(1) - c, g.k);                           // SK
+  // dQ/dc = 2 Q/c - 2 Q [ c (u (a2-1) + 4/q) + (1-k)/gv ];  w = c/d2
+  const T X = F::fma(E, tx.a2m1x2, Tq * rq4);
+  const T Y = F::fma(c, X, F::fma(Ggv, tx.omk, -(gQ * QR)));
+  const T gc = F::fma(Y, T(-2), gw * inv_d2);
+  // clamp(min=0): below the horizon c = 0 -> I = 0 -> clamped to eps -> gI = 0 -> gc = 0 already
+  const T cV = gc * rv;
+  g.n[0] = F::fma(cV, Vx, g.n[0]);
+  g.n[1] = F::fma(cV, Vy, g.n[1]);
+  g.n[2] = F::fma(cV, Vz, g.n[2]);
+}
+#else
 // Co-located light and camera (everything the reference's capture emits): l = v = h, v.h = 1,
 // n.v = n.l = n.h = c.  The specular lobe collapses to a function of c alone,
 //     Q = D G / q = a2 c^2 / (Dd gv^2 q),   Dd = pi den^2 + eps, den = c2 a2 + 1 - c2,
@@ -574,6 +778,8 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
   g.n[1] = F::fma(cV, Vy, g.n[1]);
   g.n[2] = F::fma(cV, Vz, g.n[2]);
 }
+
+#endif  // SV_COLOC_V2
 
 // General light/camera pair.
 template <typename T, int MODE, bool WANT_POW>
@@ -676,7 +882,16 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[
     gt[6 + c] = gs * ax.dpow[4 + c];
   }
   // a2 = alpha^2, k = alpha/2 + eps, alpha = rough^2
-  const T galpha = F::fma(g.a2, ax.alpha + ax.alpha, g.k * T(0.5));
+  T ga2 = g.a2, gk = g.k;
+#if SV_COLOC_V2
+  if (COLOC) {
+    // dL/da2 = sT/a2 - 2 SA (a2 = 0: the reference's dD/da2 = 1/Dd is finite, but then rough = 0 and the roughness
+    // channel's chain factor 2 rough dpow below is 0: any finite value will do);  dL/dk = -2 SK
+    ga2 = F::fma(g.a2, T(-2), F::sel(F::ge(T(0), tx.a2), T(0), g.sT * F::rcp(tx.a2)));
+    gk = g.k * T(-2);
+  }
+#endif
+  const T galpha = F::fma(ga2, ax.alpha + ax.alpha, gk * T(0.5));
   gt[5] = galpha * (ax.rough + ax.rough) * ax.dpow[3];
   // n = m/|m|
   const T ndg = F::fma(tx.n[0], g.n[0], F::fma(tx.n[1], g.n[1], tx.n[2] * g.n[2]));

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
   {
     const int row = int(pc / P.res);
     const int col = int(pc - (long long)row * P.res);
-    texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+    texel_position_rcp(row + P.row_offset, col, float(P.res), P.inv_res, P.size, tx.px, tx.py);
   }
   texel_prologue(t, pw, tx, ax);
   Grads<float> g;
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(kThreads) norm_l2_kernel(const Params P) {
   {
     const int row = int(pc / P.res);
     const int col = int(pc - (long long)row * P.res);
-    texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+    texel_position_rcp(row + P.row_offset, col, float(P.res), P.inv_res, P.size, tx.px, tx.py);
   }
   texel_prologue(raw, pw, tx, ax);
   Grads<float> g;
@@ -813,7 +813,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         row = int(pc / P.res);
         col = int(pc - (long long)row * P.res);
       }
-      texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+      texel_position_rcp(row + P.row_offset, col, float(P.res), P.inv_res, P.size, tx.px, tx.py);
     }
 #if SV_STREAM_ONLY
     tx.px = t[0]; ax.mx = t[1];
@@ -1093,7 +1093,7 @@ __device__ __forceinline__ void tile_consumer2(const Params& P, const float4* __
           row = int(q / P.res);
           col = int(q - (long long)row * P.res);
         }
-        texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, px[l], py[l]);
+        texel_position_rcp(row + P.row_offset, col, float(P.res), P.inv_res, P.size, px[l], py[l]);
       }
       tx.px = T(px[0], px[1]);
       tx.py = T(py[0], py[1]);
@@ -1429,7 +1429,7 @@ __device__ __forceinline__ void tile_consumer_ts(const Params& P, const float4* 
         row = int(pc / P.res);
         col = int(pc - (long long)row * P.res);
       }
-      texel_position_rcp(row + P.row_offset, col, P.inv_res, P.size, tx.px, tx.py);
+      texel_position_rcp(row + P.row_offset, col, float(P.res), P.inv_res, P.size, tx.px, tx.py);
     }
 #if SV_STREAM_ONLY
     tx.px = tt[0]; ax.mx = tt[1];

@@ -180,6 +180,18 @@ void dispatch(int coloc, int mode, T* tex, const T* cam, const T* light, const T
 
 extern "C" {
 
+// texel centres of one row/column: the reference's division (texel_position) and the kernels' corrected-reciprocal form
+void emu_positions(int res, float size, float* by_division, float* by_reciprocal) {
+  const float inv = 1.0f / float(res);
+  for (int j = 0; j < res; ++j) {
+    float px, py;
+    texel_position(j, j, res, size, px, py);
+    by_division[2 * j] = px; by_division[2 * j + 1] = py;
+    texel_position_rcp(j, j, float(res), inv, size, px, py);
+    by_reciprocal[2 * j] = px; by_reciprocal[2 * j + 1] = py;
+  }
+}
+
 void emu_run_f32(int coloc, int mode, float* tex, const float* cam, const float* light, const float* pw, float size,
                  int res, int row0, int rows, int W, int N, int n_total, const float* io, float* out, float* grad_tex,
                  float* grad_pow, double* loss, int outer_clamp, float* m, float* v, const double* adam) {

@@ -23,7 +23,8 @@ RTOL_RENDER = 1e-5     # BASELINE.json north_star: renders within fp32 relative 
 RTOL_GRAD = 1e-4       # gradients and optimised maps within 1e-4
 K_MAX = 10.0           # outlier bound: worst element at most K x the reference's own worst fp32 element
 
-CASES = ("coloc_32x9", "offaxis_32x9", "edges_32x9", "edges_offaxis_32x9", "wellcond_32x9", "coloc_24x16", "light_32x9")
+CASES = ("coloc_32x9", "offaxis_32x9", "edges_32x9", "edges_offaxis_32x9", "wellcond_32x9", "coloc_24x16", "light_32x9",
+         "coloc_40x9", "offaxis_48x9")      # the last two: non-power-of-two resolutions through the TMA kernel
 
 
 def golden(name):
@@ -52,6 +53,18 @@ def rel_quantile(x, ref, q=0.999):
     return float(np.quantile(err, q))
 
 
+def record_margin(what, **numbers):
+    """Append one parity measurement to the margins file (JSON lines) named by SVBRDF_PARITY_MARGINS — the GPU runs set it
+    to gpurun_out/..., the committed copy is profiles/r02_parity_margins.json.  No-op when the variable is unset."""
+    path = os.environ.get("SVBRDF_PARITY_MARGINS")
+    if not path:
+        return
+    import json
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "a") as f:
+        f.write(json.dumps({"what": what, **{k: (float(v) if v is not None else None) for k, v in numbers.items()}}) + "\n")
+
+
 def check_against_arbiter(x, ref32, ref64, rtol, what, floor=1e-6, min_fraction=0.999, strict=False, pure_relative=False):
     """Assert the parity metrics with the fp64 reference result as arbiter; returns the numbers.
 
@@ -64,6 +77,10 @@ def check_against_arbiter(x, ref32, ref64, rtol, what, floor=1e-6, min_fraction=
     """
     e_x, e_ref = max_err(x, ref64), max_err(ref32, ref64)
     frac, frac_ref = pass_fraction(x, ref64, rtol), pass_fraction(ref32, ref64, rtol)
+    record_margin(what, rtol=rtol, e_x=e_x, e_ref=e_ref, ratio=e_x / max(e_ref, 1e-300), frac=frac, frac_ref=frac_ref,
+                  p999_rel=rel_quantile(x, ref64) if pure_relative else None,
+                  p999_rel_ref=rel_quantile(ref32, ref64) if pure_relative else None, k_max=K_MAX, floor=floor,
+                  min_fraction=1.0 if strict else min_fraction)
     assert np.isfinite(np.asarray(x)).all(), f"{what}: non-finite values"
     assert e_x <= K_MAX * e_ref + floor, f"{what}: max err {e_x:.3e} vs reference fp32 noise {e_ref:.3e}"
     need = 1.0 if strict else min(min_fraction, frac_ref - 0.001)

@@ -143,3 +143,25 @@ def test_map_plane_layout_round_trip():
     import pytest
     with pytest.raises(RuntimeError, match="CUDA"):
         maps.encode_u8(th.zeros(9, 4, 4))
+
+
+def test_texel_positions_are_bit_identical_to_the_reference_division():
+    """The kernels form (j + 0.5)/R as a residual-corrected product with RN(1/R) (svbrdf_core.cuh texel_position_rcp);
+    it must equal the reference's fp32 division (microfacet.py:16-19) bit for bit at EVERY resolution, power of two or
+    not: all R <= 2048, then a spread of larger ones up to 16384."""
+    import ctypes
+
+    import numpy as np
+    import torch as th
+
+    from tests import hostemu
+    L = hostemu.lib()
+    sizes = list(range(1, 2049)) + [2049, 2500, 3000, 3071, 4095, 4096, 4097, 5000, 6144, 8191, 8192, 10000, 16383, 16384]
+    for res in sizes:
+        a = np.empty(2 * res, dtype=np.float32)
+        b = np.empty(2 * res, dtype=np.float32)
+        L.emu_positions(res, ctypes.c_float(6.848), a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(a, b), res
+        if res in (40, 48, 1100, 4096):          # and the division form is torch's: the reference's own expression
+            t = ((th.arange(res, dtype=th.float32) + 0.5) / res - 0.5) * 6.848
+            assert np.array_equal(a[0::2], t.numpy()) and np.array_equal(a[1::2], -t.numpy())
