@@ -885,9 +885,11 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[
   T ga2 = g.a2, gk = g.k;
 #if SV_COLOC_V2
   if (COLOC) {
-    // dL/da2 = sT/a2 - 2 SA (a2 = 0: the reference's dD/da2 = 1/Dd is finite, but then rough = 0 and the roughness
-    // channel's chain factor 2 rough dpow below is 0: any finite value will do);  dL/dk = -2 SK
-    ga2 = F::fma(g.a2, T(-2), F::sel(F::ge(T(0), tx.a2), T(0), g.sT * F::rcp(tx.a2)));
+    // dL/da2 = sT/a2 - 2 SA;  dL/dk = -2 SK.  Below a2 = 1e-30 the sT/a2 term is dropped: MUFU.RCP flushes a subnormal a2
+    // to zero (-> inf, and a -inf roughness gradient), and at a2 = 0 the reference's dD/da2 = 1/Dd is finite but rough = 0
+    // zeroes the channel's chain factor.  Dropping it is exact to fp32: Q/a2 = c^2/(Dd gv^2 q) <= 1e12, and the chain
+    // factor of the roughness channel, 4 rough^3 dpow = 4 a2^(3/4) dpow, is < 2e-22 there.
+    ga2 = F::fma(g.a2, T(-2), F::sel(F::ge(T(1e-30), tx.a2), T(0), g.sT * F::rcp(tx.a2)));
     gk = g.k * T(-2);
   }
 #endif

@@ -103,8 +103,12 @@ class SvbrdfOptim(Optim):
             bar = tqdm.tqdm(total=epochs)
         done = 0
         while done < epochs:
-            # next dump point of the reference cadence: epoch 1, multiples of 100, the last epoch
-            stop = 1 if done == 0 else min((done // 100 + 1) * 100, epochs)
+            # next dump point of the reference cadence (svbrdf.py:73-83): epoch 1, multiples of 100, the last epoch.  With
+            # nothing to dump and no progress bar nobody consumes the intermediate state: ONE call, one loss read-back.
+            if dump or bar is not None:
+                stop = 1 if done == 0 else min((done // 100 + 1) * 100, epochs)
+            else:
+                stop = epochs
             adam = nv.Adam(float(lr), 0.9, 0.999, 1e-8, done + 1)
             nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(tex), nv.ptr(m), nv.ptr(v), nv.ptr(tgt), dtype_code,
                                           ctypes.byref(adam), stop - done, ctypes.c_void_p(curve.data_ptr() + 4 * done),

@@ -21,7 +21,8 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL_RENDER = 1e-5     # BASELINE.json north_star: renders within fp32 relative tolerance 1e-5
 RTOL_GRAD = 1e-4       # gradients and optimised maps within 1e-4
-K_MAX = 10.0           # outlier bound: worst element at most K x the reference's own worst fp32 element
+K_MAX = 3.0            # outlier bound: worst element at most K x the reference's own worst fp32 element (K = 2-3;
+                       # measured ratios: profiles/r02_parity_margins.json — all <= 2.4 except the one call that passes k_max)
 
 CASES = ("coloc_32x9", "offaxis_32x9", "edges_32x9", "edges_offaxis_32x9", "wellcond_32x9", "coloc_24x16", "light_32x9",
          "coloc_40x9", "offaxis_48x9")      # the last two: non-power-of-two resolutions through the TMA kernel
@@ -65,24 +66,25 @@ def record_margin(what, **numbers):
         f.write(json.dumps({"what": what, **{k: (float(v) if v is not None else None) for k, v in numbers.items()}}) + "\n")
 
 
-def check_against_arbiter(x, ref32, ref64, rtol, what, floor=1e-6, min_fraction=0.999, strict=False, pure_relative=False):
+def check_against_arbiter(x, ref32, ref64, rtol, what, floor=1e-6, min_fraction=0.999, strict=False, pure_relative=False, k_max=None):
     """Assert the parity metrics with the fp64 reference result as arbiter; returns the numbers.
 
     * finite everywhere;
-    * outlier bound: max|x-f64|/max|f64| <= K_MAX x (the reference's own fp32 figure) + floor;
+    * outlier bound: max|x-f64|/max|f64| <= k_max (default K_MAX) x (the reference's own fp32 figure) + floor;
     * >= 99.9 % of elements within rtol*|f64| + rtol*max|f64| (or as many as the reference's own
       fp32 manages on that fixture, minus 0.1 % — clamp-edge fixtures are ill-conditioned for both);
     * strict=True (well-conditioned fixture): every element within tolerance;
     * pure_relative=True (renders): additionally the 99.9th percentile of |x-f64|/|f64| <= rtol.
     """
+    k_max = K_MAX if k_max is None else k_max
     e_x, e_ref = max_err(x, ref64), max_err(ref32, ref64)
     frac, frac_ref = pass_fraction(x, ref64, rtol), pass_fraction(ref32, ref64, rtol)
     record_margin(what, rtol=rtol, e_x=e_x, e_ref=e_ref, ratio=e_x / max(e_ref, 1e-300), frac=frac, frac_ref=frac_ref,
                   p999_rel=rel_quantile(x, ref64) if pure_relative else None,
-                  p999_rel_ref=rel_quantile(ref32, ref64) if pure_relative else None, k_max=K_MAX, floor=floor,
+                  p999_rel_ref=rel_quantile(ref32, ref64) if pure_relative else None, k_max=k_max, floor=floor,
                   min_fraction=1.0 if strict else min_fraction)
     assert np.isfinite(np.asarray(x)).all(), f"{what}: non-finite values"
-    assert e_x <= K_MAX * e_ref + floor, f"{what}: max err {e_x:.3e} vs reference fp32 noise {e_ref:.3e}"
+    assert e_x <= k_max * e_ref + floor, f"{what}: max err {e_x:.3e} vs reference fp32 noise {e_ref:.3e}"
     need = 1.0 if strict else min(min_fraction, frac_ref - 0.001)
     assert frac >= need, f"{what}: only {frac * 100:.4f}% of elements within rtol={rtol:g} (reference fp32: {frac_ref * 100:.4f}%)"
     if pure_relative:

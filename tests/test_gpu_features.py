@@ -120,12 +120,34 @@ def test_combined_loss_against_reference_golden(path):
     assert float(l2) == pytest.approx(float(g["loss_image"]), rel=1e-5)
     assert float(lf) == pytest.approx(float(g["loss_feature"]), rel=1e-4)
     gfeat, = th.autograd.grad(lf, tex, retain_graph=True)
+    gnorm, = th.autograd.grad(lf, norm, retain_graph=True)      # what the feature network hands the render backward
     (l2 + lf).backward()
+    # (1) the native backward against the oracle's autograd for the SAME upstream gradient (fp64 arbiter, fp32 oracle's own
+    # noise beside it): this is the kernel check proper and uses the tolerances of tests/parity.py
+    from oracle import torch_port as tp
+    from tests import parity
+    cl_cpu = [th.from_numpy(g[k]) for k in ("cam", "light", "power")]
+    up = gnorm.detach().cpu()
+    oracle = {}
+    for dt in (th.float32, th.float64):
+        sc = tp.Scene(res, cl_cpu[0], cl_cpu[1], cl_cpu[2], synth.IM_SIZE_CM, dt)
+        t = th.from_numpy(g["tex"]).to(dt).requires_grad_(True)
+        img = tp.shade(sc, t)
+        nrm = (img - th.tensor(MEAN, dtype=dt)[None, :, None, None]) / th.tensor(STD, dtype=dt)[None, :, None, None]
+        total = (nrm * up.to(dt)).sum() + tp.l2_loss(img, th.from_numpy(g["targets"]).to(dt))
+        oracle[dt], = th.autograd.grad(total, t)
+    parity.check_against_arbiter(tex.grad.cpu().numpy(), oracle[th.float32].numpy(), oracle[th.float64].numpy(), parity.RTOL_GRAD,
+                                 f"{os.path.basename(path)[:-4]} consumer backward, same upstream gradient")
+    # (2) end to end against the reference's own run (CPU VGG19).  The seeded random-weight VGG19 sits between the two
+    # fp32 renders and the render backward and amplifies their ~1e-7 differences: two builds of this library whose
+    # gradients both sit inside the fp32 oracle's own error for a FIXED upstream (gpurun visit r02 f3: no element outside
+    # the mixed tolerance for either) score 0.9923 and > 0.999 here.  Hence a looser pass fraction than (1); recorded.
     for got, ref in ((tex.grad, g["grad"]), (gfeat, g["grad_feature"])):
         ref = th.from_numpy(ref).to(DEV)
-        # mixed tolerance of tests/parity.py: ill-conditioned GGX-peak texels are fp32 noise in the reference itself
         ok = (got - ref).abs() <= 1e-4 * ref.abs() + 2e-4 * ref.abs().max()
-        assert float(ok.float().mean()) > 0.999
+        parity.record_margin(f"{os.path.basename(path)[:-4]} end-to-end grad vs reference golden", frac=float(ok.float().mean()),
+                             mean_err=float((got - ref).abs().mean() / ref.abs().max()))
+        assert float(ok.float().mean()) > 0.98
         assert float((got - ref).abs().mean()) < 2e-5 * float(ref.abs().max())
     # drop-in class semantics: forward(x) == forward_normalized(normalize(x)) and equals the oracle's restatement
     with th.no_grad():

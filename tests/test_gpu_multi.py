@@ -29,7 +29,7 @@ def test_view_sharded_single_rank_equals_fused():
     losses = vs.optim(int(g["epochs"]), float(g["lr"]))
     np.testing.assert_allclose(np.array(losses), g["loss_f64"], rtol=5e-5)
     parity.check_against_arbiter(vs.textures.cpu().numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "view-sharded maps",
-                                 floor=2e-4, min_fraction=0.998)
+                                 floor=2e-4, min_fraction=0.999)
 
 
 def _free_port():
@@ -92,13 +92,13 @@ def test_two_rank_nccl_view_and_material_sharding(tmp_path):
     assert th.equal(a["tex"], b["tex"]) and a["losses"] == b["losses"]          # replicas stay bit-identical
     np.testing.assert_allclose(np.array(a["losses"]), g["loss_f64"], rtol=5e-5)
     parity.check_against_arbiter(a["tex"].numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "2-rank view-sharded maps",
-                                 floor=2e-4, min_fraction=0.998)
+                                 floor=2e-4, min_fraction=0.999)
     # peer-push mode: replicas bit-identical by construction, same optimisation as the NCCL mode
     assert th.equal(a["p2p_tex"], b["p2p_tex"]) and a["p2p_losses"] == b["p2p_losses"]
     assert th.equal(a["uni_tex"], a["p2p_tex"]) and th.equal(b["uni_tex"], a["p2p_tex"])     # multicast == unicast all-gather
     print("NVLS multicast used:", a["mc"], b["mc"])
     np.testing.assert_allclose(np.array(a["p2p_losses"]), g["loss_f64"], rtol=5e-5)
     parity.check_against_arbiter(a["p2p_tex"].numpy(), g["maps_f32"], g["maps_f64"], parity.RTOL_GRAD, "2-rank peer-push maps",
-                                 floor=2e-4, min_fraction=0.998)
+                                 floor=2e-4, min_fraction=0.999)
     assert a["mine"] == [0, 2, 4] and b["mine"] == [1, 3]
     assert a["all"] == b["all"] and len(a["all"]) == 5 and all(np.isfinite(a["all"]))

@@ -38,13 +38,18 @@ def test_double_is_exact(name):
 def test_float_within_reference_noise(name, noise):
     g = parity.golden(name)
     strict = name.startswith("wellcond")
+    # the noise model charges EVERY MUFU result the documented worst-case error (+-2^-22) with a random sign — a bound on
+    # what the device may do, well above what it does (GPU margins: profiles/r02_parity_margins.json) — so the
+    # single-worst-element bound keeps K = 10 here; the device tests use parity.K_MAX
+    k = 10.0 if noise else None
     out = E.run(E.MODE_RENDER, g["tex_gt"][0], *_args(g), noise=noise)["out"]
-    parity.check_against_arbiter(out, g["target"], g["render_gt_f64"], parity.RTOL_RENDER, f"{name} render", strict=strict, pure_relative=True)
+    parity.check_against_arbiter(out, g["target"], g["render_gt_f64"], parity.RTOL_RENDER, f"{name} render", strict=strict, pure_relative=True,
+                                 k_max=k)
     l2 = E.run(E.MODE_L2, g["tex0"][0], *_args(g, "power"), io=g["target"], outer_clamp=True, noise=noise)
-    parity.check_against_arbiter(l2["grad_tex"], g["grad0_f32"][0], g["grad0_f64"][0], parity.RTOL_GRAD, f"{name} grad", strict=strict)
+    parity.check_against_arbiter(l2["grad_tex"], g["grad0_f32"][0], g["grad0_f64"][0], parity.RTOL_GRAD, f"{name} grad", strict=strict, k_max=k)
     assert l2["loss"] == pytest.approx(float(g["loss_f64"][0]), rel=1e-5)
     v = E.run(E.MODE_VJP, np.clip(g["tex0"][0], -1, 1), *_args(g), io=g["grad_img"], noise=noise)
-    parity.check_against_arbiter(v["grad_tex"], g["vjp_tex_f32"][0], g["vjp_tex_f64"][0], parity.RTOL_GRAD, f"{name} vjp", strict=strict)
+    parity.check_against_arbiter(v["grad_tex"], g["vjp_tex_f32"][0], g["vjp_tex_f64"][0], parity.RTOL_GRAD, f"{name} vjp", strict=strict, k_max=k)
 
 
 def _adam_run(g, dtype, epochs, noise=False):
@@ -74,7 +79,7 @@ def test_fused_adam_float_within_tolerance(name, noise):
     maps, losses = _adam_run(g, np.float32, int(g["epochs"]), noise)
     np.testing.assert_allclose(losses, g["loss_f64"], rtol=2e-5)
     e_x, e_ref, frac = parity.check_against_arbiter(maps, g["maps_f32"][0], g["maps_f64"][0], parity.RTOL_GRAD, f"{name} maps",
-                                                    floor=2e-4, min_fraction=0.998)
+                                                    floor=2e-4, min_fraction=0.999)
 
 
 def test_row_band_equals_full():
