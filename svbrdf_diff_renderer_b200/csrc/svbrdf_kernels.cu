@@ -50,13 +50,20 @@ constexpr int kPrefetch = 2;           // texel_kernel: lights of io data in fli
 //    r01_s3_variants_chunk_lights.txt): 4 lights per slot are 4.1 % faster than 3 at 64 and at 16 lights, 3 are 2.7 %
 //    faster at 9 lights (9 = 4+4+1: the odd light takes the guarded partial-slot path); 5, 6, 8 are slower than 4.
 //    The launcher picks 3 or 4 from the light count (pick_chunk).
-template <int CW, int LANES, int MAXNREG, int CHUNK = 3>
+//  * PW = warps of the producer's slice of the CTA.  PW = 1: the producer is the last warp of the last warpgroup and all
+//    warps keep the launch-time register count.  PW = 4: the producer sits in a warpgroup of its own (3 of its warps
+//    retire at once), so the register file can be re-split with setmaxnreg — the producer warpgroup drops to 24
+//    registers, the CW consumer warps (a multiple of 4: the same number on each of the 4 SM sub-partitions, which 15 + 1
+//    is not) rise from the launch-time MAXNREG to CREGS.
+template <int CW, int LANES, int MAXNREG, int CHUNK = 3, int PW = 1, int CREGS = 0>
 struct TileShape {
   static constexpr int kCW = CW;
   static constexpr int kLanes = LANES;
+  static constexpr int kPW = PW;
+  static constexpr int kConsumerRegs = CREGS;        // setmaxnreg.inc target of the consumer warpgroups (PW = 4)
   static constexpr int kTile = 32 * CW * LANES;      // texels per tile
   static constexpr int kConsumers = 32 * CW;         // consumer threads
-  static constexpr int kThreads = 32 * (CW + 1);     // + the producer warp
+  static constexpr int kThreads = 32 * (CW + PW);    // + the producer warp(group)
   static constexpr int kChunk = CHUNK;               // lights per ring slot
   static constexpr int kSlotPlanes = 3 * CHUNK > 9 ? 3 * CHUNK : 9;
   static constexpr int kSlotBytes = kSlotPlanes * kTile * 4;   // one ring slot: 9 plane segments (12 with 4-light slots)
@@ -86,8 +93,14 @@ struct TileShape {
 #ifndef SV_PACKED_DEFAULT
 #define SV_PACKED_DEFAULT 0
 #endif
-typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 3> ScalarShape;
-typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 4> ScalarShape4;
+#ifndef SV_PRODUCER_WARPS
+#define SV_PRODUCER_WARPS 1
+#endif
+#ifndef SV_CONSUMER_REGS
+#define SV_CONSUMER_REGS 0
+#endif
+typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 3, SV_PRODUCER_WARPS, SV_CONSUMER_REGS> ScalarShape;
+typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 4, SV_PRODUCER_WARPS, SV_CONSUMER_REGS> ScalarShape4;
 typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG, 3> PackedShape;
 // SV_STASH: park the values only the epilogue needs (raw texel, gamma derivatives, normal reconstruction:
 // 29 floats per texel) in shared memory while the light loop runs, instead of in registers: the compiler
@@ -1746,8 +1759,13 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
   const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
 
   if (tid >= SH::kConsumers) {
+    if (SH::kPW == 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+      if (tid >= SH::kConsumers + 32) return;                      // only the first warp of the producer warpgroup works
+    }
     tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);    // whole warp, uniform control flow
   } else {
+    if (SH::kPW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SH::kConsumerRegs));
     if (SH::kLanes == 2) {
       if (coloc) tile_consumer2<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
       else tile_consumer2<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);

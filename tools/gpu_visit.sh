@@ -22,7 +22,7 @@ if [ -n "${LIBS:-}" ]; then
     if [ "$lib" = base ]; then unset SVBRDF_B200_LIB; else export SVBRDF_B200_LIB=$C/libsvbrdf_b200_$lib.so; fi
     for cfg in "${CF[@]}"; do
       echo "== lib $lib $cfg" | tee -a $OUT/variants_$TAG.txt
-      timeout 200 python tools/kernel_bench.py $cfg --variants "tma1" 2>&1 | grep -v '^{' | tail -1 | tee -a $OUT/variants_$TAG.txt
+      timeout ${KB_TIMEOUT:-120} python tools/kernel_bench.py $cfg --variants "tma1" 2>&1 | grep -v '^{' | tail -1 | tee -a $OUT/variants_$TAG.txt
     done
   done
   done
