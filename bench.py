@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--no-view-sharded", action="store_true", help="skip the view-sharded (strong-scaling) leg")
     ap.add_argument("--vs-res", type=int, default=4096)
     ap.add_argument("--vs-lights", type=int, default=256)
+    ap.add_argument("--no-config3", action="store_true", help="skip the 4096^2 x 64 three-roof leg (BASELINE configs[2]; N=1 only)")
+    ap.add_argument("--no-material-batch", action="store_true", help="skip the 38-material batch (BASELINE configs[3])")
+    ap.add_argument("--materials", type=int, default=38)
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-this-GPU side line (N=1 only)")
+    ap.add_argument("--no-descriptor", action="store_true", help="skip the L2 + descriptor-loss step (BASELINE configs[1] wording; N=1 only)")
     return ap.parse_args()
 
 
@@ -195,8 +200,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": args.res * args.res * args.lights / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, {"reference_path": "oracle/torch_port.py (op-for-op restatement of the reference's torch path; "
-                                                       "the reference itself is pure Python and does not travel to the GPU box)"}),
+        "config": config_dict(args),
+        "reference_path": "oracle/torch_port.py (op-for-op restatement of the reference's torch path, pinned bit for bit to the unmodified "
+                          "reference by tests/test_oracle_pin.py; the reference itself is pure Python and does not travel to the GPU box)",
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -400,6 +406,21 @@ def run_b200_arm(args):
         th.cuda.empty_cache()
         view = view_sharded_bench(args, dev, world, rank, barrier)
 
+    # ---- BASELINE configs[3]: the material batch, round-robin over the ranks (every N) ----
+    batch = None
+    if not args.no_material_batch:
+        batch = material_batch_bench(args, dev, world, rank, barrier)
+
+    # ---- single-GPU extra legs: configs[2] three-roof line, L2 + descriptor step, torch-eager side line ----
+    config3 = descriptor = eager = None
+    if world == 1:
+        if not args.no_config3:
+            config3 = config3_bench(dev, local)
+        if not args.no_descriptor:
+            descriptor = descriptor_bench(dev)
+        if not args.no_eager:
+            eager = eager_bench(dev)
+
     # ---- cpu baseline (rank 0 only, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -412,6 +433,7 @@ def run_b200_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "view_sharded": view, "clocks": clk.summary(),
+            "config3": config3, "material_batch": batch, "config2_l2_plus_descriptor": descriptor, "reference_cuda_eager": eager,
             "gpu_launches": gpu_launches,
             "gpu_launches_what": "tile_kernel<L2Adam> launches in the timed region: one persistent launch per material and <=64 epochs (loss reduction fused: last CTA finalises each epoch)",
         }
@@ -475,6 +497,218 @@ def view_sharded_bench(args, dev, world, rank, barrier):
     best = max((out[k] for k in ("nccl", "peer_push") if k in out), key=lambda d: d["value"])
     out["value"] = best["value"]
     out["ms_per_epoch"] = best["ms_per_epoch"]
+    return out
+
+
+def load_json(*parts):
+    try:
+        with open(os.path.join(ROOT, *parts)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def config3_bench(dev, local):
+    """BASELINE configs[2]: the fused step at 4096^2 texels x 64 lights (1.07e9 samples, 16.5 GB streamed per epoch),
+    reported against the three roofs of SURVEY.md section 8(d): HBM (984 B per texel), MUFU (16 lanes per SM and clock) and
+    instruction issue (4 warp instructions per SM and clock).  Instructions and MUFU operations per sample are EXECUTED
+    counts from the committed ncu capture of this kernel (profiles/r02_inst_mix_4096x64_v2.json, tools/ncu_inst_mix.py);
+    the clock is the one NVML reports while the leg runs."""
+    import ctypes
+
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import _native as nv
+    from svbrdf_diff_renderer_b200 import synth
+    res, n, epochs = 4096, 64, 6
+    P = res * res
+    L = nv.lib()
+    cl = [c.to(dev) for c in synth.calibration(n)]
+    r = pkg.Microfacet(res, n, synth.IM_SIZE_CM, cl, dev)
+    with th.no_grad():
+        tgt = r.eval(synth.random_textures(res, 1).to(dev)).contiguous()
+    tex = synth.random_textures(res, 2)[0].to(dev)
+    m, v = th.zeros_like(tex), th.zeros_like(tex)
+    curve = th.zeros(64, device=dev)
+    ws, geom, stream = r._workspace(), r._geom(r._pow), nv.stream_ptr(dev)
+
+    def run(k, first):
+        a = nv.Adam(LR, 0.9, 0.999, 1e-8, first)
+        nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(tex), nv.ptr(m), nv.ptr(v), nv.ptr(tgt), 0, ctypes.byref(a), k, nv.ptr(curve), None,
+                                      nv.ptr(ws), stream), "l2_adam_run")
+    run(3, 1)                                                # warm-up epochs
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        run(epochs, 4)
+        e1.record()
+        th.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / epochs
+    losses = curve[:epochs].tolist()
+    clocks = clk.summary()
+    mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965
+    peaks = load_json("MEASURED_PEAKS.json") or {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    mix = load_json("profiles", "r02_inst_mix_4096x64_v2.json") or {}
+    instr, mufu = mix.get("issue_slots_per_sample"), mix.get("mufu_per_sample")
+    samples = P * n
+    sps = samples / (ms * 1e-3)
+    sms = 148
+    out = {"workload": "fused step (clamp+render+L2+backward+Adam), 4096x4096 texels, 64 co-located lights, fp32 targets (BASELINE.json configs[2])",
+           "epochs_timed": epochs, "ms_per_epoch": ms, "samples_per_s": sps, "loss_first_last": [losses[0], losses[-1]],
+           "launches": epochs, "l2": "every epoch streams 16.5 GB through a 126 MB L2", "clocks": clocks,
+           "hbm": {"bytes_per_texel": 216 + 12 * n, "achieved_gbs": (216 + 12 * n) * P / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback"}}
+    out["hbm"]["frac"] = out["hbm"]["achieved_gbs"] / hbm_peak
+    fracs = {"hbm": out["hbm"]["frac"]}
+    if instr and mufu:
+        mufu_peak = sms * 16 * mhz * 1e6                    # MUFU results per second
+        issue_peak = sms * 128 * mhz * 1e6                  # thread instructions per second (4 schedulers x 32 lanes per SM)
+        out["mufu"] = {"per_sample": mufu, "achieved_per_s": mufu * sps, "peak_per_s": mufu_peak, "frac": mufu * sps / mufu_peak}
+        out["issue"] = {"thread_instructions_per_sample": instr, "achieved_per_s": instr * sps, "peak_per_s": issue_peak,
+                        "frac": instr * sps / issue_peak}
+        out["counts_source"] = "profiles/r02_inst_mix_4096x64_v2.json (ncu capture of this kernel at this size: smsp__inst_executed.sum x 32 / samples; MUFU from the SASS source counters)"
+        out["sm_mhz_used"] = mhz
+        fracs.update(mufu=out["mufu"]["frac"], issue=out["issue"]["frac"])
+    out["binding_roof"] = max(fracs, key=fracs.get)
+    out["fractions"] = fracs
+    del tgt, tex, m, v
+    th.cuda.empty_cache()
+    return out
+
+
+def eager_bench(dev):
+    """The reference's torch path run EAGERLY on this GPU (what a user of the reference gets on the same B200 with
+    `device=cuda:0`, scripts.py:68): the pinned op-for-op port (oracle/torch_port.py) — eval + MSELoss + backward +
+    torch.optim.Adam.step per iteration, 745 aten calls.  Side line, not the --impl reference arm."""
+    from oracle import torch_port as tp
+    from svbrdf_diff_renderer_b200 import synth
+    out = {}
+    for res, iters in ((256, 20), (1024, 10)):
+        n = 9
+        cl = synth.calibration(n)
+        sc = tp.Scene(res, cl[0], cl[1], cl[2], synth.IM_SIZE_CM, th.float32, device=dev)
+        with th.no_grad():
+            tgt = tp.shade(sc, synth.random_textures(res, 1).to(dev))
+        tex = synth.random_textures(res, 2).to(dev).requires_grad_(True)
+        opt = th.optim.Adam([tex], lr=LR, betas=(0.9, 0.999))
+
+        def step():
+            loss = tp.l2_loss(tp.shade(sc, tex.clamp(-1, 1)), tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(3):
+            step()
+        th.cuda.synchronize()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            loss = step()
+        e1.record()
+        th.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[f"{res}x{res}x{n}"] = {"ms_per_iter": ms, "samples_per_s": res * res * n / (ms * 1e-3), "iters": iters, "loss": float(loss)}
+        del sc, tgt, tex, opt
+        th.cuda.empty_cache()
+    out["what"] = "oracle/torch_port.py (bit-identical to the reference on CPU) on cuda:0, torch eager fp32, loss left on the device"
+    return out
+
+
+def descriptor_bench(dev):
+    """BASELINE configs[1] as worded — "L2 + descriptor loss" — at 1024^2 x 9: one SvbrdfOptim.optim_with_features step
+    (render + normalise + L2 in one native kernel each way, VGG19 feature network in torch/cuDNN, torch Adam), split into
+    the native kernels' time and the rest by a second timing of the native part alone.  The pretrained VGG19 weights are a
+    download (absent here): seeded random weights of the same architecture, same arithmetic cost."""
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import synth
+    from torchvision.models import vgg19
+    res, n, steps = 1024, 9, 3
+    cl = [c.to(dev) for c in synth.calibration(n)]
+    r = pkg.Microfacet(res, n, synth.IM_SIZE_CM, cl, dev)
+    with th.no_grad():
+        tgt = r.eval(synth.random_textures(res, 1).to(dev)).contiguous()
+    th.manual_seed(7)
+    vgg = pkg.VGGLoss(dev, net=vgg19(weights=None).features)
+    vgg.load(tgt)
+    o = pkg.SvbrdfOptim(dev, r)
+    o.load_targets(tgt)
+    o.init_from_tex(synth.random_textures(res, 2).to(dev))
+    o.optim_with_features(1, LR, vgg, 0.1)                   # warm-up (cuDNN algorithm selection)
+    th.cuda.synchronize()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    li, lf = o.optim_with_features(steps, LR, vgg, 0.1)
+    e1.record()
+    th.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    # the native share: the same forward + backward kernels with a stand-in upstream gradient instead of the network
+    tex = o.textures.detach().clone().requires_grad_(True)
+    up = None
+    e0.record()
+    for _ in range(steps):
+        norm, l2 = r.eval_normalized(tex.clamp(-1, 1), vgg.mean, vgg.std, tgt)
+        up = th.ones_like(norm) if up is None else up
+        th.autograd.grad([norm, l2], [tex], [up, th.ones_like(l2)])
+    e1.record()
+    th.cuda.synchronize()
+    ms_native = e0.elapsed_time(e1) / steps
+    out = {"workload": "optim_perpixel step with L2 + 0.1 x descriptor (VGG19) loss, 1024x1024 x 9 lights", "steps": steps, "ms_per_step": ms_step,
+           "ms_native_render_fwd_bwd": ms_native, "ms_vgg_and_torch": ms_step - ms_native, "loss_image": li[-1], "loss_feature": lf[-1],
+           "tf32": bool(th.backends.cudnn.allow_tf32), "weights": "seeded random VGG19 (the pretrained file is a download)",
+           "what": "ms_native = svbrdf_render_norm_l2_fwd + _bwd (+ clamp and a ones_like per step); the remainder is the cuDNN VGG19 forward/backward, "
+                   "torch.optim.Adam and autograd bookkeeping"}
+    del vgg, o, tgt
+    th.cuda.empty_cache()
+    return out
+
+
+def material_batch_bench(args, dev, world, rank, barrier):
+    """BASELINE configs[3]: a batch of independent materials at 1024^2 x 9, 20 epochs each, dealt round-robin over the ranks
+    (38 on 8 GPUs -> 5,5,5,5,5,5,4,4: ideal speed-up 7.6x) through sharding.optimise_materials — uploads of every material's
+    targets and start maps from pinned host memory and the download of its result included.  The targets travel as what
+    they are on disk, uint8 PNG bytes (imageio.py:18-19; decoded in-kernel, bit-identical to the host's /255); the fp32
+    upload is timed beside it."""
+    import torch.distributed as dist
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import sharding, synth
+    res, n, M = 1024, 9, args.materials
+    cl = [c.to(dev) for c in synth.calibration(n)]
+    r = pkg.Microfacet(res, n, synth.IM_SIZE_CM, cl, dev)
+    mine = sharding.round_robin(M, world, rank)
+    host = {}
+    for i in mine:                                           # untimed: synthesise this rank's inputs, park them in pinned host memory
+        with th.no_grad():
+            t = r.eval(synth.random_textures(res, 1000 + 2 * i).to(dev))
+        u8 = (t * 255).round().to(th.uint8)
+        host[i] = {"u8": u8.cpu().pin_memory(), "f32": (u8.float() / 255).cpu().pin_memory(),
+                   "tex0": synth.random_textures(res, 1001 + 2 * i).pin_memory()}
+        del t, u8
+    out = {"materials": M, "res": res, "lights": n, "epochs_per_material": JOB_EPOCHS, "materials_per_rank": [len(sharding.round_robin(M, world, k)) for k in range(world)],
+           "ideal_speedup_vs_1_gpu": M / max(len(sharding.round_robin(M, world, k)) for k in range(world))}
+    results = {}
+    for key in ("u8", "f32"):
+        def make_problem(i, key=key):
+            return r, host[i][key].to(dev, non_blocking=True), host[i]["tex0"].to(dev, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        mine_out, finals = sharding.optimise_materials(M, make_problem, JOB_EPOCHS, LR, dev, to_host=True)
+        th.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = th.tensor([dt], device=dev, dtype=th.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        bytes_up = sum(host[i][key].numel() * host[i][key].element_size() + host[i]["tex0"].numel() * 4 for i in mine)
+        results[key] = {"wall_s": dt, "materials_per_s": M / dt, "samples_per_s": M * JOB_EPOCHS * res * res * n / dt,
+                        "h2d_bytes_this_rank": bytes_up, "final_loss_mean": float(sum(finals) / len(finals))}
+        del mine_out
+    out["uint8_targets"], out["fp32_targets"] = results["u8"], results["f32"]
+    out["what"] = ("wall clock (max over ranks) of sharding.optimise_materials: per material upload targets + start maps from pinned host memory "
+                   "(prefetched on a copy stream while the previous material runs), 20 fused epochs in one persistent launch, maps back to the host")
+    del host
+    th.cuda.empty_cache()
     return out
 
 

@@ -47,13 +47,15 @@ class Scene:
     fp32 oracle or the fp64 arbiter (same code, every attribute in double).
     """
 
-    def __init__(self, res, cam, light, power, size, dtype=th.float32, rows=None):
+    def __init__(self, res, cam, light, power, size, dtype=th.float32, rows=None, device=None):
         n = cam.shape[0]
         self.res, self.n, self.dtype = res, n, dtype
         ticks = th.arange(res, dtype=th.float32)
         ticks = ((ticks + 0.5) / res - 0.5) * size          # fp32 like the reference, then widened
         gx, gy = th.meshgrid(ticks, ticks, indexing="xy")
         plane = th.stack((gx, -gy, th.zeros_like(gx)), 2).permute(2, 0, 1).to(dtype)
+        if device is not None:                               # the reference on `cuda:0` (scripts.py:68): bench.py's eager side line
+            plane, cam, light, power = plane.to(device), cam.to(device), light.to(device), power.to(device)
         if rows is not None:                                 # row band [r0, r1) of the full image
             plane = plane[:, rows[0]:rows[1], :]
         h, w = plane.shape[1], plane.shape[2]

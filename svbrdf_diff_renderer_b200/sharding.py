@@ -275,23 +275,57 @@ class PeerShardedOptim:
         return self.losses
 
 
-def optimise_materials(n_materials, make_problem, epochs, lr, device, group=None):
+def optimise_materials(n_materials, make_problem, epochs, lr, device, group=None, to_host=False, prefetch=True):
     """Material-sharded driver: ``make_problem(i)`` -> ``(renderer, targets, start_textures)`` for material i.
 
     Returns ``{material index: (final loss, optimised textures)}`` for this rank's materials and the list of
     final losses of ALL materials (gathered on the host — the only communication of this mode).
+
+    ``prefetch``: material i+1's ``make_problem`` (typically host->device uploads of its targets and start maps) runs on a
+    copy stream while material i is being optimised, so the PCIe transfer hides behind the kernel (or the other way round).
+    ``to_host``: the optimised maps are copied to pinned host memory (asynchronously) instead of being kept on the device.
     """
     from .svbrdf import SvbrdfOptim
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    device = th.device(device)
+    ids = round_robin(n_materials, world, rank)
+    main = th.cuda.current_stream(device)
+    copy = th.cuda.Stream(device) if prefetch else main
+
+    def fetch(i):
+        """make_problem under the copy stream; the tensors are handed to the main stream by an event."""
+        with th.cuda.stream(copy):
+            renderer, targets, tex0 = make_problem(i)
+            ev = copy.record_event()
+        for t in (targets, tex0):
+            if prefetch and isinstance(t, th.Tensor) and t.is_cuda:
+                t.record_stream(main)                          # allocated on the copy stream, consumed on the main one
+        return renderer, targets, tex0, ev
+
     mine = {}
-    for i in round_robin(n_materials, world, rank):
-        renderer, targets, tex0 = make_problem(i)
+    nxt = fetch(ids[0]) if ids else None
+    for k, i in enumerate(ids):
+        renderer, targets, tex0, ev = nxt
+        nxt = fetch(ids[k + 1]) if k + 1 < len(ids) else None   # enqueued before this material's kernels: overlaps them
+        main.wait_event(ev)
         opt = SvbrdfOptim(device, renderer)
         opt.load_targets(targets)
         opt.init_from_tex(tex0)
-        losses = opt.optim(epochs, lr, None, False, progress=False)
-        mine[i] = (losses[-1] if losses else float("nan"), opt.textures.detach())
+        curve = opt.optim(epochs, lr, None, False, progress=False, read_back=False)
+        maps = opt.textures.detach()
+        if to_host:
+            pinned = th.empty(maps.shape, dtype=maps.dtype, pin_memory=True)
+            pinned.copy_(maps, non_blocking=True)
+            maps = pinned
+        mine[i] = (curve, maps)
+    # one synchronisation for the whole batch: the loss curves are read after everything has been enqueued
+    def last(curve):
+        if isinstance(curve, th.Tensor):
+            return float(curve[-1]) if curve.numel() else float("nan")
+        return curve[-1] if curve else float("nan")
+    mine = {i: (last(c), m) for i, (c, m) in mine.items()}
+    th.cuda.synchronize(device)
     final = {i: l for i, (l, _) in mine.items()}
     if world > 1:
         gathered = [None] * world

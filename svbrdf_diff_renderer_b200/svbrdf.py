@@ -62,9 +62,11 @@ class SvbrdfOptim(Optim):
         return self.loss_l2(predicts, tg)
 
     # ---- the loop (svbrdf.py:44-83) --------------------------------------------------------------
-    def optim(self, epochs, lr, svbrdf_obj, optim_light, fused=True, progress=True):
+    def optim(self, epochs, lr, svbrdf_obj, optim_light, fused=True, progress=True, read_back=True):
         """Run ``epochs`` Adam iterations.  ``fused=False`` takes the mode-B route instead
-        (native render fwd/bwd under autograd + torch.optim.Adam), the path any non-L2 loss uses."""
+        (native render fwd/bwd under autograd + torch.optim.Adam), the path any non-L2 loss uses.
+        ``read_back=False`` (no dumps, no progress bar): nothing is synchronised — the loss curve is returned as a device
+        tensor and ``self.losses`` is filled lazily, so a batch driver can enqueue many materials back to back."""
         dump = svbrdf_obj is not None and hasattr(svbrdf_obj, "optimize_dir")
         tmp_dir = None
         if dump:
@@ -113,6 +115,9 @@ class SvbrdfOptim(Optim):
             nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(tex), nv.ptr(m), nv.ptr(v), nv.ptr(tgt), dtype_code,
                                           ctypes.byref(adam), stop - done, ctypes.c_void_p(curve.data_ptr() + 4 * done),
                                           nv.ptr(pow_state), nv.ptr(ws), nv.stream_ptr(self.device)), "svbrdf_l2_adam_run")
+            if not read_back and not dump and bar is None:
+                self.losses = curve[:epochs]             # device tensor; the caller reads it when it needs it
+                return self.losses
             seg = curve[done:stop].tolist()          # one device->host sync per segment
             self.losses.extend(seg)
             if bar is not None:

@@ -48,13 +48,26 @@ def main():
         thread_total += t
         samples_total += s
     per = lambda w: w * 32.0 / a.samples
+    # the un-instrumented timing pass of the same capture (raw page): what the issue-slot roof is computed from — the
+    # source-page counters come from an instrumented replay whose barrier-polling loops spin longer
+    raw_rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True,
+                                                         check=True).stdout)))
+    rh, rd = raw_rows[0], raw_rows[2]
+    rawv = lambda k: float(rd[rh.index(k)]) if k in rh and rd[rh.index(k)] not in ("", "no data") else None
+    timed = {k: rawv(k) for k in ("smsp__inst_executed.sum", "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
+                                  "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.max.pct_of_peak_sustained_active",
+                                  "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                                  "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum")}
     out = {"kernel": kernel, "report": a.rep, "samples": a.samples, "warp_instructions": warp_total,
            "thread_instructions_per_sample_full_warps": per(warp_total), "thread_instructions_per_sample_active_threads": thread_total / a.samples,
            "per_class": {k: per(v) for k, v in per_cls.most_common()}, "per_opcode": {k: per(v) for k, v in per_op.most_common()},
            "mufu_per_sample": per(sum(v for k, v in per_op.items() if k.startswith("MUFU"))),
+           "timed_pass": timed,
+           "issue_slots_per_sample": (timed["smsp__inst_executed.sum"] * 32.0 / a.samples) if timed.get("smsp__inst_executed.sum") else per(warp_total),
            "note": "warp instructions x 32 / samples: an issue slot is spent per warp instruction whatever its active mask"}
     lines = [f"# Executed instruction mix — {kernel}", f"# {a.rep}: {warp_total:,} warp instructions for {a.samples:,.0f} pixel.light samples",
-             "", f"issue slots (warp instr x 32) per sample: **{out['thread_instructions_per_sample_full_warps']:.1f}**; MUFU per sample: **{out['mufu_per_sample']:.2f}**", "",
+             "", f"issue slots (warp instr x 32) per sample: **{out['issue_slots_per_sample']:.1f}** in the timing pass (smsp__inst_executed.sum), "
+                 f"{out['thread_instructions_per_sample_full_warps']:.1f} in the instrumented source-counter pass; MUFU per sample: **{out['mufu_per_sample']:.2f}**", "",
              "| pipe class | thread instr / sample | share |", "|---|---|---|"]
     for k, v in per_cls.most_common():
         lines.append(f"| {k} | {per(v):.2f} | {100.0 * v / warp_total:.1f} % |")
