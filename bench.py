@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-view-sharded", action="store_true", help="skip the view-sharded (strong-scaling) leg")
     ap.add_argument("--vs-res", type=int, default=4096)
     ap.add_argument("--vs-lights", type=int, default=256)
+    ap.add_argument("--no-config5", action="store_true", help="skip the full-size view-sharded leg (8192^2 x 256, uint8 targets)")
     ap.add_argument("--no-config3", action="store_true", help="skip the 4096^2 x 64 three-roof leg (BASELINE configs[2]; N=1 only)")
     ap.add_argument("--no-material-batch", action="store_true", help="skip the 38-material batch (BASELINE configs[3])")
     ap.add_argument("--materials", type=int, default=38)
@@ -400,11 +401,16 @@ def run_b200_arm(args):
     clk.__exit__(None, None, None)
 
     # ---- view-sharded mode: ONE material, lights split over the ranks, NCCL all-reduce of the gradient ----
-    view = None
+    view = config5 = None
+    del mats
+    th.cuda.empty_cache()
     if not args.no_view_sharded:
-        del mats
-        th.cuda.empty_cache()
-        view = view_sharded_bench(args, dev, world, rank, barrier)
+        view = view_sharded_bench(args, dev, world, rank, barrier, args.vs_res, args.vs_lights, th.float32,
+                                  f"one material, {args.vs_res}^2 texels x {args.vs_lights} lights, fp32 targets (round 1's strong-scaling leg)")
+    if not args.no_config5:
+        config5 = view_sharded_bench(args, dev, world, rank, barrier, 8192, 256, th.uint8,
+                                     "BASELINE.json configs[4] at full size: one material, 8192^2 texels x 256 light views, uint8 targets "
+                                     "(51.5 GB in total: fits one B200)")
 
     # ---- BASELINE configs[3]: the material batch, round-robin over the ranks (every N) ----
     batch = None
@@ -433,7 +439,7 @@ def run_b200_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "view_sharded": view, "clocks": clk.summary(),
-            "config3": config3, "material_batch": batch, "config2_l2_plus_descriptor": descriptor, "reference_cuda_eager": eager,
+            "config5_view_sharded": config5, "config3": config3, "material_batch": batch, "config2_l2_plus_descriptor": descriptor, "reference_cuda_eager": eager,
             "gpu_launches": gpu_launches,
             "gpu_launches_what": "tile_kernel<L2Adam> launches in the timed region: one persistent launch per material and <=64 epochs (loss reduction fused: last CTA finalises each epoch)",
         }
@@ -442,22 +448,55 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-def view_sharded_bench(args, dev, world, rank, barrier):
-    """Strong scaling of one material: `vs_res`^2 texels x `vs_lights` lights in total, lights sharded over the ranks
-    (SURVEY.md §8(e)).  Two transports are timed on the same problem:
-      * "peer_push": the collective is fused into the kernels — svbrdf_l2_grad_push stores each tile's partial gradient
-        straight into the owner rank's slot over NVLink while shading, svbrdf_reduce_adam_push reduces + Adam-updates the
-        owned texels and stores the new parameters into every replica (N>1 only);
-      * "nccl": per row band svbrdf_l2_grad -> async NCCL all_reduce -> replicated svbrdf_adam_apply."""
+def render_targets(res, cl_cpu, lights, rows, dev, dtype, gt, chunk=4):
+    """Synthetic targets of light range `lights` = (start, end), rows `rows` = (r0, r1): rendered `chunk` lights at a time by
+    the native forward kernel (a full [256,3,8192,8192] fp32 stack is 206 GB), quantised to the PNG bytes when `dtype` is
+    uint8 (imageio.py:18-19 read side: x/255).  Untimed set-up."""
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import synth
+    s0, s1 = lights
+    r0, r1 = rows
+    out = th.empty(s1 - s0, 3, r1 - r0, res, dtype=dtype, device=dev)
+    for a in range(s0, s1, chunk):
+        b = min(a + chunk, s1)
+        r = pkg.Microfacet(res, b - a, synth.IM_SIZE_CM, [cl_cpu[0][a:b].to(dev), cl_cpu[1][a:b].to(dev), cl_cpu[2].to(dev)], dev)
+        with th.no_grad():
+            img = r.eval(gt)[:, :, r0:r1, :]
+            out[a - s0:b - s0] = (img * 255).round().to(th.uint8) if dtype == th.uint8 else img
+        del img, r
+    return out
+
+
+def view_sharded_bench(args, dev, world, rank, barrier, res, n, dtype, label):
+    """Strong scaling of ONE material: `res`^2 texels x `n` lights in total.  Transports timed on the
+    same problem (same seeds at every N, so `loss_first_last` must agree across N):
+      * N = 1: the fused single-GPU kernel (svbrdf_l2_adam_run: the denominator of the speed-up) and the unfused
+        svbrdf_l2_grad + svbrdf_adam_apply pair the NCCL mode is built from;
+      * "nccl": lights sharded; per row band svbrdf_l2_grad -> async NCCL all_reduce -> replicated svbrdf_adam_apply;
+      * "peer_push": lights sharded; the reduce-scatter and the all-gather are fused into the kernels over NVLink peer
+        memory (svbrdf_l2_grad_push / svbrdf_reduce_adam_push);
+      * "hybrid_BxS": B row bands x S light shards — peer_push inside each band's group of S ranks, nothing between bands."""
+    import ctypes
+
     import torch.distributed as dist
+    import svbrdf_diff_renderer_b200 as pkg
+    from svbrdf_diff_renderer_b200 import _native as nv
     from svbrdf_diff_renderer_b200 import sharding, synth
-    res, n = args.vs_res, args.vs_lights
     cl = synth.calibration(n)
     gt = synth.random_textures(res, 1).to(dev)
     tex0 = synth.random_textures(res, 2)
     epochs = 5
-    out = {"unit": UNIT, "scaling": "strong", "res": res, "lights_total": n, "epochs_timed": epochs,
+    tb = 1 if dtype == th.uint8 else 4
+    out = {"workload": label, "unit": UNIT, "scaling": "strong", "res": res, "lights_total": n, "epochs_timed": epochs,
+           "target_dtype": "u8" if dtype == th.uint8 else "f32", "target_bytes_total": n * 3 * res * res * tb,
            "gradient_bytes_per_epoch": 9 * res * res * 4}
+
+    def reduce_max(ms):
+        if world > 1:
+            t = th.tensor([ms], device=dev, dtype=th.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     def time_optim(opt):
         opt.optim(2, LR)                                 # warm-up (NCCL channels / symmetric-memory barriers, kernels)
@@ -467,23 +506,49 @@ def view_sharded_bench(args, dev, world, rank, barrier):
         losses = opt.optim(epochs, LR)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = th.tensor([ms], device=dev, dtype=th.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = reduce_max(e0.elapsed_time(e1))
         return {"value": res * res * n * epochs / (ms * 1e-3), "ms_per_epoch": ms / epochs, "loss_first_last": [losses[0], losses[-1]]}
 
+    start, end = sharding.split_range(n, world, rank)
+    tgt = render_targets(res, cl, (start, end), (0, res), dev, dtype, gt)
+    out["lights_per_gpu"] = end - start
+
+    if world == 1:
+        # the fused single-GPU kernel: what one B200 does on this problem (the speed-up's denominator)
+        r = pkg.Microfacet(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev)
+        L = nv.lib()
+        tex = tex0[0].to(dev).clone()
+        m, v = th.zeros_like(tex), th.zeros_like(tex)
+        curve = th.zeros(64, device=dev)
+        geom, ws = r._geom(r._pow), r._workspace()
+
+        def run(k, first):
+            a = nv.Adam(LR, 0.9, 0.999, 1e-8, first)
+            nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(tex), nv.ptr(m), nv.ptr(v), nv.ptr(tgt), nv.target_dtype_code(tgt), ctypes.byref(a), k,
+                                          nv.ptr(curve), None, nv.ptr(ws), nv.stream_ptr(dev)), "l2_adam_run")
+        run(2, 1)
+        th.cuda.synchronize()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        run(epochs, 3)
+        e1.record()
+        th.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        ls = curve[:epochs].tolist()
+        out["fused_single_gpu"] = {"value": res * res * n * epochs / (ms * 1e-3), "ms_per_epoch": ms / epochs, "loss_first_last": [ls[0], ls[-1]],
+                                   "what": "svbrdf_l2_adam_run: the fused render+L2+backward+Adam kernel, one launch per epoch at this size"}
+        del tex, m, v, r
+
     vs = sharding.ViewShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev, bands=4)
-    with th.no_grad():                                   # this rank's targets only
-        tgt = vs.renderer.eval(gt)
     vs.load_targets(tgt)
+    if world == 1:
+        del tgt                                          # ViewShardedOptim keeps band-major copies
     vs.init_from_tex(tex0)
-    out["lights_per_gpu"] = vs.n_local
     out["nccl"] = time_optim(vs)
     out["nccl"]["what"] = ("4 row bands: svbrdf_l2_grad -> async NCCL all_reduce(SUM) of the band gradient (overlaps the next band) -> "
                            "replicated svbrdf_adam_apply") if world > 1 else "1 GPU: svbrdf_l2_grad + svbrdf_adam_apply per band, no collective"
     del vs
+    th.cuda.empty_cache()
     if world > 1:
         ps = sharding.PeerShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev)
         ps.load_targets(tgt)
@@ -493,10 +558,29 @@ def view_sharded_bench(args, dev, world, rank, barrier):
         out["peer_push"]["what"] = ("svbrdf_l2_grad_push (TMA-loads each tile's textures from the owner's replica over NVLink, stores the partial "
                                     "gradient into the owner's slot: all-gather and reduce-scatter fused into the gradient kernel) -> barrier -> "
                                     "svbrdf_reduce_adam_push (owner-side reduce + sharded Adam, local) -> barrier")
-        del ps
-    best = max((out[k] for k in ("nccl", "peer_push") if k in out), key=lambda d: d["value"])
-    out["value"] = best["value"]
-    out["ms_per_epoch"] = best["ms_per_epoch"]
+        del ps, tgt
+        th.cuda.empty_cache()
+        for shards in (2, 4):
+            if shards >= world or world % shards:
+                continue
+            hy = sharding.HybridShardedOptim(res, n, synth.IM_SIZE_CM, [c.to(dev) for c in cl], dev, light_shards=shards)
+            htgt = render_targets(res, cl, (hy.start, hy.end), hy.band, dev, dtype, gt)
+            hy.load_targets(htgt)
+            del htgt
+            hy.init_from_tex(tex0)
+            key = f"hybrid_{hy.n_bands}x{shards}"
+            out[key] = time_optim(hy)
+            out[key]["what"] = (f"{hy.n_bands} row bands x {shards} light shards: peer_push inside each band's group of {shards} ranks "
+                                f"({(hy.end - hy.start)} lights x {hy.band[1] - hy.band[0]} rows per GPU), no traffic between bands")
+            del hy
+            th.cuda.empty_cache()
+    keys = [k for k in out if isinstance(out[k], dict) and "ms_per_epoch" in out[k]]
+    best = max(keys, key=lambda k: out[k]["value"])
+    out["best"] = best
+    out["value"] = out[best]["value"]
+    out["ms_per_epoch"] = out[best]["ms_per_epoch"]
+    del gt
+    th.cuda.empty_cache()
     return out
 
 

@@ -125,7 +125,9 @@ typedef struct svbrdf_peers_t {
 
 /* svbrdf_l2_grad fused with the reduce-scatter: the partial gradient of every tile is STORED STRAIGHT INTO THE
  * OWNER'S receive slot over NVLink while the next tile is being shaded (no local gradient tensor, no NCCL call).
- * `tex` is this rank's replica (peers->tex[peers->rank]); geom holds this rank's light shard; full image only. */
+ * `tex` is this rank's replica (peers->tex[peers->rank]); geom holds this rank's light shard.  geom may describe a row
+ * band (rows < res, row_offset): the band's rows*res texels are then what the peer group shares — ownership, receive
+ * slots and the replicas are all band-relative (2-D decomposition: row bands x light shards, one peer group per band). */
 int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void* target, int32_t target_dtype,
                         int32_t n_total, const svbrdf_peers_t* peers, float* loss_out, void* workspace,
                         svbrdf_stream_t stream);

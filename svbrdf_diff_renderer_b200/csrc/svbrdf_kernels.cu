@@ -2139,8 +2139,11 @@ static int launch_tile(Params P, cudaStream_t st) {
     return launch_tile_ts<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 #endif
 #if SV_ENABLE_PACKED
-  if (env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
+  // the peer-sharded modes own texels in units of ScalarShape::kTile (check_peers): the packed shape's 448-texel tiles would
+  // straddle owners, so the development override does not apply to them
+  if (P.push_world == 0 && env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
 #endif
+  static_assert(ScalarShape4::kTile == ScalarShape::kTile, "peer ownership granularity is one tile of either scalar shape");
   if (pick_chunk(P.n_lights) == 4) return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape4>(P, st);
   return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 }
@@ -2289,7 +2292,7 @@ int svbrdf_l2_adam_step(const svbrdf_geom_t* geom, float* tex, float* m, float* 
 }
 
 static int check_peers(const svbrdf_peers_t* p) {
-  if (!p || p->world < 1 || p->world > 8 || p->rank < 0 || p->rank >= p->world || p->chunk <= 0 || p->chunk % 480 != 0) return SVBRDF_E_BADARG;
+  if (!p || p->world < 1 || p->world > 8 || p->rank < 0 || p->rank >= p->world || p->chunk <= 0 || p->chunk % ScalarShape::kTile != 0) return SVBRDF_E_BADARG;
   for (int r = 0; r < p->world; ++r)
     if (!p->recv[r] || !p->tex[r]) return SVBRDF_E_BADARG;
   return 0;
@@ -2299,8 +2302,10 @@ int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void*
                         const svbrdf_peers_t* peers, float* loss_out, void* workspace, svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (int e = check_peers(peers)) return e;
-  if (!tex || !target || !workspace || n_total < geom->n_lights || geom->rows != geom->res || geom->row_offset != 0) return SVBRDF_E_BADARG;
-  if ((long long)peers->world * peers->chunk < (long long)geom->res * geom->res) return SVBRDF_E_BADARG;
+  // a row band (rows < res, row_offset > 0) is legal: the band's texels are what the peers share (2-D decomposition: row
+  // bands x light shards, one peer group per band); ownership, receive slots and `tex` are all relative to the band
+  if (!tex || !target || !workspace || n_total < geom->n_lights || geom->plane_stride != 0) return SVBRDF_E_BADARG;
+  if ((long long)peers->world * peers->chunk < (long long)geom->rows * geom->res) return SVBRDF_E_BADARG;
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = target;

@@ -179,7 +179,10 @@ class PeerShardedOptim:
 
     TILE = 480      # ownership granularity = tile size of the gradient kernel (include/svbrdf_b200.h)
 
-    def __init__(self, res, n_total, size, cl, device, group=None, multicast=True, pull=True):
+    def __init__(self, res, n_total, size, cl, device, group=None, multicast=True, pull=True, band=None, loss_group=None):
+        """``band=(r0, r1)``: the peer group shares only rows [r0, r1) of the image (targets ``[n_local,3,r1-r0,R]``, maps
+        ``[1,9,r1-r0,R]``) — the building block of the 2-D decomposition (``HybridShardedOptim``).  ``loss_group``: the group
+        the per-epoch loss shares are summed over (default: ``group``; the hybrid mode passes the world group)."""
         import torch.distributed._symmetric_memory as symm
         from . import _native as nv
         from .microfacet import Microfacet
@@ -198,7 +201,14 @@ class PeerShardedOptim:
         self.renderer = Microfacet(res, self.n_local, size,
                                    [cl[0][self.start:self.end].to(self.device), cl[1][self.start:self.end].to(self.device), cl[2].to(self.device)],
                                    self.device)
-        self.texels = res * res
+        self.band = (0, res) if band is None else (int(band[0]), int(band[1]))
+        if not (0 <= self.band[0] < self.band[1] <= res):
+            raise ValueError(f"bad row band {band} for a {res}-row image")
+        self.rows = self.band[1] - self.band[0]
+        self.loss_group = self.group if loss_group is None else loss_group
+        self.texels = self.rows * res
+        if self.texels % 4:
+            raise RuntimeError("peer-push mode needs the band's texel count to be a multiple of 4")
         per = -(-self.texels // self.world)
         self.chunk = -(-per // self.TILE) * self.TILE
         name = self.group.group_name
@@ -222,16 +232,21 @@ class PeerShardedOptim:
         # pull mode (default): no all-gather — the gradient kernel reads each tile's textures from its owner over NVLink
         self.pull = bool(pull)
         self.peers.pull_tex = 1 if self.pull else 0
-        self.ws = nv.workspace(res, res, self.device)
+        self.ws = nv.workspace(res, self.rows, self.device)
         self.losses = []
 
     def load_targets(self, local_targets):
-        if tuple(local_targets.shape) != (self.n_local, 3, self.res, self.res):
-            raise RuntimeError(f"rank {self.rank}: targets must be [{self.n_local},3,{self.res},{self.res}]")
+        """``[n_local,3,rows,R]``: this rank's light shard of the (band of the) target stack, float32 or uint8."""
+        if tuple(local_targets.shape) != (self.n_local, 3, self.rows, self.res):
+            raise RuntimeError(f"rank {self.rank}: targets must be [{self.n_local},3,{self.rows},{self.res}]")
         self.targets = local_targets.to(self.device).contiguous()
 
     def init_from_tex(self, textures):
-        full = textures.detach().to(device=self.device, dtype=th.float32).contiguous().clone()
+        """Start maps ``[1,9,R,R]`` (the band is cut out here) or ``[1,9,rows,R]``; the group's rank 0 wins."""
+        full = textures.detach().to(device=self.device, dtype=th.float32)
+        if full.shape[2] == self.res and self.rows != self.res:
+            full = full[:, :, self.band[0]:self.band[1], :]
+        full = full.contiguous().clone()
         dist.broadcast(full, src=dist.get_global_rank(self.group, 0), group=self.group)
         self.tex_sym.copy_(full.view(-1))
         th.cuda.synchronize(self.device)
@@ -243,7 +258,7 @@ class PeerShardedOptim:
         the owned chunks are gathered (one collective, outside the optimisation loop)."""
         full = self.tex_sym.view(9, self.texels)
         if not self.pull:
-            return full.view(1, 9, self.res, self.res)
+            return full.view(1, 9, self.rows, self.res)
         mine = th.zeros(9, self.chunk, dtype=th.float32, device=self.device)
         lo = self.rank * self.chunk
         hi = min(lo + self.chunk, self.texels)
@@ -251,14 +266,14 @@ class PeerShardedOptim:
             mine[:, :hi - lo] = full[:, lo:hi]
         parts = [th.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(parts, mine, group=self.group)
-        return th.cat(parts, 1)[:, :self.texels].reshape(1, 9, self.res, self.res).contiguous()
+        return th.cat(parts, 1)[:, :self.texels].reshape(1, 9, self.rows, self.res).contiguous()
 
     def optim(self, epochs, lr):
         nv, L = self.nv, self.nv.lib()
         m = th.zeros(9 * self.chunk, dtype=th.float32, device=self.device)
         v = th.zeros_like(m)
         curve = th.zeros(max(epochs, 1), dtype=th.float32, device=self.device)
-        geom = self.renderer._geom(self.renderer._pow)
+        geom = self.renderer._geom(self.renderer._pow, rows=self.rows, row_offset=self.band[0])
         stream = nv.stream_ptr(self.device)
         for epoch in range(epochs):
             nv.check(L.svbrdf_l2_grad_push(ctypes.byref(geom), nv.ptr(self.tex_sym), nv.ptr(self.targets), nv.target_dtype_code(self.targets),
@@ -270,8 +285,79 @@ class PeerShardedOptim:
                      "svbrdf_reduce_adam_push")
             self.h_tex.barrier(channel=0)                   # every replica holds the new parameters
         if epochs > 0:
-            dist.all_reduce(curve, op=dist.ReduceOp.SUM, group=self.group)      # loss shares add; once per run
+            dist.all_reduce(curve, op=dist.ReduceOp.SUM, group=self.loss_group)      # loss shares add; once per run
         self.losses = curve[:epochs].tolist()
+        return self.losses
+
+
+def hybrid_layout(world: int, light_shards: int, rank: int):
+    """2-D decomposition of one material over ``world`` ranks: ``bands = world // light_shards`` row bands x ``light_shards``
+    light shards.  Rank r works on band ``r // light_shards`` with light shard ``r % light_shards``; the ranks of one band
+    are consecutive (one peer group per band).  Returns ``(band index, shard index, [[ranks of band 0], [ranks of band 1], ...])``."""
+    if light_shards < 1 or world % light_shards:
+        raise ValueError(f"{world} ranks cannot be split into groups of {light_shards} light shards")
+    if not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    bands = world // light_shards
+    groups = [list(range(b * light_shards, (b + 1) * light_shards)) for b in range(bands)]
+    return rank // light_shards, rank % light_shards, groups
+
+
+class HybridShardedOptim:
+    """One material on ``world = bands x light_shards`` GPUs: the image is cut into ``bands`` row bands, every band is
+    view-sharded over a peer group of ``light_shards`` ranks (``PeerShardedOptim`` on the band: gradient exchange fused
+    into the kernels over NVLink), and bands never talk to each other (texels are independent; only the loss is summed).
+
+    Why: in the 1-D view-sharded mode every rank runs the per-texel prologue/epilogue, pulls 9 texture planes and pushes a
+    36-byte partial gradient for ALL texels, amortised over only N/world lights — at 8 ranks that fixed work is what
+    bounds the scaling (profiles/r01_peer_phase_timing_8gpu.txt).  With b bands it shrinks by b, and the exchange stays
+    inside groups of world/b ranks.  ``light_shards = world`` is the 1-D mode; ``light_shards = 1`` would be pure pixel-band
+    sharding (no exchange at all) and is refused here — that is not a view-sharded run."""
+
+    def __init__(self, res, n_total, size, cl, device, light_shards, multicast=True, pull=True):
+        if not dist.is_initialized():
+            raise RuntimeError("HybridShardedOptim needs an initialised process group (NCCL, one process per GPU)")
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if light_shards < 2:
+            raise ValueError("light_shards must be >= 2 (1 = pixel-band sharding, not a view-sharded run)")
+        self.band_index, self.shard_index, groups = hybrid_layout(world, light_shards, rank)
+        self.n_bands = len(groups)
+        pgs = [dist.new_group(ranks=g) for g in groups]       # every rank creates every group (collective)
+        self.group = pgs[self.band_index]
+        self.band = row_bands(res, self.n_bands)[self.band_index] if self.n_bands > 1 else (0, res)
+        if len(row_bands(res, self.n_bands)) != self.n_bands:
+            raise RuntimeError(f"a {res}-row image cannot be cut into {self.n_bands} bands")
+        self.inner = PeerShardedOptim(res, n_total, size, cl, device, group=self.group, multicast=multicast, pull=pull, band=self.band,
+                                      loss_group=dist.group.WORLD)
+        self.res, self.n_total, self.device = res, n_total, th.device(device)
+        self.start, self.end, self.n_local = self.inner.start, self.inner.end, self.inner.n_local
+        self.renderer = self.inner.renderer
+
+    def load_targets(self, local_targets):
+        """``[n_local,3,rows,R]``: lights ``start:end`` of rows ``band[0]:band[1]``."""
+        self.inner.load_targets(local_targets)
+
+    def init_from_tex(self, textures):
+        full = textures.detach().to(device=self.device, dtype=th.float32).contiguous().clone()
+        dist.broadcast(full, src=0)                            # world rank 0 wins, then each band group takes its rows
+        self.inner.init_from_tex(full)
+
+    @property
+    def textures(self):
+        """``[1,9,R,R]`` assembled from the bands (one all-gather over the world, outside the optimisation loop)."""
+        mine = self.inner.textures                              # [1,9,rows,R], identical within the band group
+        world = dist.get_world_size()
+        bands = row_bands(self.res, self.n_bands)
+        rows_max = max(b[1] - b[0] for b in bands)
+        pad = th.zeros(1, 9, rows_max, self.res, dtype=th.float32, device=self.device)
+        pad[:, :, :mine.shape[2]] = mine
+        parts = [th.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        shards = world // self.n_bands
+        return th.cat([parts[b * shards][:, :, :bands[b][1] - bands[b][0]] for b in range(self.n_bands)], 2).contiguous()
+
+    def optim(self, epochs, lr):
+        self.losses = self.inner.optim(epochs, lr)
         return self.losses
 
 

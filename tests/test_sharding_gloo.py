@@ -25,6 +25,14 @@ def test_split_helpers():
         assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
         sizes = [e - s for s, e in got]
         assert max(sizes) - min(sizes) <= 1
+    # 2-D decomposition: consecutive ranks share a band, light shard = rank within the band's group
+    assert sharding.hybrid_layout(8, 2, 5) == (2, 1, [[0, 1], [2, 3], [4, 5], [6, 7]])
+    assert sharding.hybrid_layout(8, 4, 5) == (1, 1, [[0, 1, 2, 3], [4, 5, 6, 7]])
+    assert sharding.hybrid_layout(4, 4, 3) == (0, 3, [[0, 1, 2, 3]])
+    with pytest.raises(ValueError):
+        sharding.hybrid_layout(8, 3, 0)
+    cover = sorted((b, s_) for b, s_, _ in (sharding.hybrid_layout(8, 2, r) for r in range(8)))
+    assert cover == [(b, s_) for b in range(4) for s_ in range(2)]
     assert [len(sharding.round_robin(38, 8, r)) for r in range(8)] == [5, 5, 5, 5, 5, 5, 4, 4]
     assert sorted(sum((sharding.round_robin(38, 8, r) for r in range(8)), [])) == list(range(38))
     for res, b in ((1024, 4), (24, 4), (5, 8), (32, 1)):
