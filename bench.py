@@ -150,6 +150,10 @@ def cpu_reference_run(res, lights, steps, warmup, budget_s=150.0):
     from svbrdf_diff_renderer_b200 import synth
 
     cores = os.cpu_count() or 1
+    try:                                                     # the GPU arm binds the process to its GPU's NUMA node: give the CPU baseline every core back
+        os.sched_setaffinity(0, set(range(cores)))
+    except Exception:
+        pass
     th.set_num_threads(cores)
     cl = synth.calibration(lights)
     gt, t0 = synth.random_textures(res, 1), synth.random_textures(res, 2)
@@ -228,6 +232,8 @@ def run_b200_arm(args):
         raise RuntimeError("bench.py --impl b200 needs a GPU (the CUDA path has no CPU fallback)")
     th.cuda.set_device(local)
     dev = th.device("cuda", local)
+    from svbrdf_diff_renderer_b200 import sharding as _sh
+    numa = _sh.bind_to_gpu_cpus(local)                     # pinned host buffers end up on the GPU's own NUMA node
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -353,9 +359,9 @@ def run_b200_arm(args):
         for i in range(2):
             e2e_step(i)
         ms_e = timed(e2e_step, e2e_steps)
-        e2e = {"value": samples_per_step * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": stage.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
-               "what": "every step re-uploads its [N,3,R,R] fp32 targets from pinned host memory, runs the fused step, reads the loss back"}
+        e2e_f32 = {"value": samples_per_step * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": stage.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
+                   "what": "same protocol with the targets uploaded as the reference's float32 stack (x/255 done on the host)"}
 
         # the same per-step protocol with the targets kept as what they are on disk — uint8 PNG bytes (imageio.py:18-19);
         # the fused kernel divides by 255 itself (bit-identical to the host division), a quarter of the upload
@@ -373,30 +379,41 @@ def run_b200_arm(args):
         for i in range(2):
             e2e_step_u8(i)
         ms_u8 = timed(e2e_step_u8, e2e_steps)
-        e2e["uint8_targets"] = {"value": samples_per_step * world * e2e_steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": stage_u8.numel(),
-                                "d2h_bytes_per_step": 4, "ms_per_step": ms_u8 / e2e_steps,
-                                "what": "same protocol, targets uploaded as uint8 (the PNG bytes), decoded in-kernel"}
+        e2e = {"value": samples_per_step * world * e2e_steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": stage_u8.numel(),
+               "d2h_bytes_per_step": 4, "steps": e2e_steps, "ms_per_step": ms_u8 / e2e_steps,
+               "what": "every step re-uploads its [N,3,R,R] targets from pinned host memory as what they are on disk and what optim_perpixel ingests "
+                       "by default — uint8 PNG bytes (imageio.py:18-19), divided by 255 in-kernel, bit-identical to the host division — runs the fused "
+                       "step through the C ABI and reads the loss back",
+               "fp32_targets": e2e_f32}
 
         # the call a user makes: SvbrdfOptim.optim(20 epochs) on host-resident inputs, result back on the host
         host_tex0 = mats[0]["tex0"].cpu().pin_memory()
         host_out = th.empty_like(host_tex0).pin_memory()
 
-        def job(i):
-            o.load_targets(host_targets[i % 2].to(dev, non_blocking=True))
-            o.init_from_tex(host_tex0.to(dev, non_blocking=True))
-            losses = o.optim(JOB_EPOCHS, LR, None, False, progress=False)          # includes the loss-curve readback
-            host_out.copy_(o.textures.detach(), non_blocking=True)
-            th.cuda.current_stream().synchronize()
-            return losses
+        def make_job(bufs):
+            def job(i):
+                o.load_targets(bufs[i % 2].to(dev, non_blocking=True))
+                o.init_from_tex(host_tex0.to(dev, non_blocking=True))
+                losses = o.optim(JOB_EPOCHS, LR, None, False, progress=False)          # includes the loss-curve readback
+                host_out.copy_(o.textures.detach(), non_blocking=True)
+                th.cuda.current_stream().synchronize()
+                return losses
+            return job
 
-        for i in range(2):                       # both host buffers once: the device blocks they alternate between are cached afterwards
-            job(i)
         jobs = 4
-        ms_j = timed(job, jobs)
-        e2e_job = {"value": samples_per_step * world * JOB_EPOCHS * jobs / (ms_j * 1e-3), "unit": UNIT, "epochs_per_call": JOB_EPOCHS,
-                   "ms_per_call": ms_j / jobs, "h2d_bytes_per_call": stage.numel() * 4 + host_tex0.numel() * 4,
-                   "d2h_bytes_per_call": host_out.numel() * 4 + 4 * JOB_EPOCHS,
-                   "what": "SvbrdfOptim.optim(20 epochs): pinned-host targets + init maps uploaded, 20 fused epochs, maps + loss curve downloaded"}
+        res_job = {}
+        for key, bufs in (("u8", host_u8), ("f32", host_targets)):
+            job = make_job(bufs)
+            for i in range(2):                   # both host buffers once: the device blocks they alternate between are cached afterwards
+                job(i)
+            ms_j = timed(job, jobs)
+            res_job[key] = {"value": samples_per_step * world * JOB_EPOCHS * jobs / (ms_j * 1e-3), "unit": UNIT, "epochs_per_call": JOB_EPOCHS,
+                            "ms_per_call": ms_j / jobs, "h2d_bytes_per_call": bufs[0].numel() * bufs[0].element_size() + host_tex0.numel() * 4,
+                            "d2h_bytes_per_call": host_out.numel() * 4 + 4 * JOB_EPOCHS}
+        e2e_job = res_job["u8"]
+        e2e_job["what"] = ("SvbrdfOptim.optim(20 epochs): pinned-host uint8 targets (optim_perpixel's default ingest) + init maps uploaded, 20 fused "
+                           "epochs in one persistent launch, maps + loss curve downloaded")
+        e2e_job["fp32_targets"] = res_job["f32"]
 
     clk.__exit__(None, None, None)
 
@@ -440,7 +457,7 @@ def run_b200_arm(args):
             "config": config_dict(args), "iters_per_s_per_gpu": K / (ms * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_job": e2e_job, "view_sharded": view, "clocks": clk.summary(),
             "config5_view_sharded": config5, "config3": config3, "material_batch": batch, "config2_l2_plus_descriptor": descriptor, "reference_cuda_eager": eager,
-            "gpu_launches": gpu_launches,
+            "gpu_launches": gpu_launches, "cpu_affinity": numa,
             "gpu_launches_what": "tile_kernel<L2Adam> launches in the timed region: one persistent launch per material and <=64 epochs (loss reduction fused: last CTA finalises each epoch)",
         }
         emit(line)
@@ -772,9 +789,15 @@ def material_batch_bench(args, dev, world, rank, barrier):
     out = {"materials": M, "res": res, "lights": n, "epochs_per_material": JOB_EPOCHS, "materials_per_rank": [len(sharding.round_robin(M, world, k)) for k in range(world)],
            "ideal_speedup_vs_1_gpu": M / max(len(sharding.round_robin(M, world, k)) for k in range(world))}
     results = {}
-    for key in ("u8", "f32"):
+    for key in ("warm", "u8", "f32"):
         def make_problem(i, key=key):
-            return r, host[i][key].to(dev, non_blocking=True), host[i]["tex0"].to(dev, non_blocking=True)
+            return r, host[i]["u8" if key == "warm" else key].to(dev, non_blocking=True), host[i]["tex0"].to(dev, non_blocking=True)
+        if key == "warm":
+            # one untimed pass: device blocks and the pinned result buffers (cudaHostAlloc: ~1 ms per 40 MB map set) enter
+            # the caching allocators, as they would for the second batch of a long-running job
+            warm = sharding.optimise_materials(M, make_problem, 2, LR, dev, to_host=True)
+            del warm
+            continue
         barrier()
         t0 = time.perf_counter()
         mine_out, finals = sharding.optimise_materials(M, make_problem, JOB_EPOCHS, LR, dev, to_host=True)

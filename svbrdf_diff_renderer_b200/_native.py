@@ -21,7 +21,7 @@ _ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsvbrdf_b200.so")
 SOURCES = [os.path.join(CSRC, "svbrdf_kernels.cu"), os.path.join(CSRC, "svbrdf_maps.cu")]
-HEADERS = [os.path.join(CSRC, "svbrdf_core.cuh"), os.path.join(_ROOT, "include", "svbrdf_b200.h")]
+HEADERS = [os.path.join(CSRC, "svbrdf_core.cuh"), os.path.join(CSRC, "svbrdf_host.h"), os.path.join(_ROOT, "include", "svbrdf_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -937,6 +937,9 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[
 }
 
 // dL/d light_pow_c from the accumulated sum of gfp_c * fp_c (= pw_c * dL/dpw_c).
+// pw_c == 0 returns 0, which is also the reference's value: every sample of that channel is I = 0, the clamp of
+// microfacet.py:120 replaces it by eps, and autograd's clamp mask (eps <= I <= 1) blocks the gradient — so
+// dL/dpw_c = sum gI_c f_c w = 0 there too, and Adam leaves a zero light-power channel where it is in both.
 template <typename T>
 SV_HD T pow_grad(T acc, T pw) { return pw != T(0) ? acc / pw : T(0); }   // scalar only (finalisation)
 

@@ -33,6 +33,7 @@
 
 #include "../../include/svbrdf_b200.h"
 #include "svbrdf_core.cuh"
+#include "svbrdf_host.h"
 
 namespace svbrdf {
 
@@ -1904,15 +1905,41 @@ static inline size_t partial_rows(long long texels) {
 }
 
 struct Device {
+  int index = 0;
   int sms = 0;
   int smem_optin = 0;
 };
+// Attributes of the current device, queried once per device and process (the single-epoch launch path is called every
+// ~70 us; with one process per GPU on an 8-GPU box the per-launch driver queries showed up as a 17 % longer step).
+// Racing first calls write the same values.
 static int device_info(Device* d) {
+  constexpr int kMaxDev = 64;
+  static int cached_sms[kMaxDev] = {0}, cached_smem[kMaxDev] = {0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return int(e);
+  d->index = dev;
+  if (dev >= 0 && dev < kMaxDev && cached_sms[dev] > 0 && cached_smem[dev] > 0) {
+    d->sms = cached_sms[dev];
+    d->smem_optin = cached_smem[dev];
+    return 0;
+  }
   if ((e = cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return int(e);
   if ((e = cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return int(e);
+  if (dev >= 0 && dev < kMaxDev) {
+    cached_smem[dev] = d->smem_optin;
+    cached_sms[dev] = d->sms;
+  }
+  return 0;
+}
+
+// cudaFuncSetAttribute(max dynamic shared memory, carve-out) once per (kernel instantiation, device, size) instead of on
+// every launch.  `slot` is a per-instantiation static array indexed by device.
+static int set_smem_once(const void* kern, int dev, size_t smem, int* slot) {
+  if (dev >= 0 && dev < 64 && slot[dev] == int(smem)) return 0;
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
+  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
+  if (dev >= 0 && dev < 64) slot[dev] = int(smem);
   return 0;
 }
 
@@ -1994,8 +2021,8 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   const size_t smem = size_t(slots) * SH::kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
   if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
   auto kern = tile_kernel<MODE, WANT_POW, TGT, SH>;
-  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return int(e);
-  if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) return int(e);
+  static int smem_set[64] = {0};
+  if (int e = set_smem_once(reinterpret_cast<const void*>(kern), d.index, smem, smem_set)) return e;
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
   long long grid = (long long)d.sms * ctas_per_sm;
   if (grid > n_tiles) grid = n_tiles;
@@ -2033,6 +2060,9 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
     return 0;
   }
   if (trace) fprintf(stderr, "[svbrdf] tile_kernel mode %d lanes %d tile %d slots %d smem %zu grid %lld\n", MODE, SH::kLanes, SH::kTile, slots, smem, grid);
+  // the finish tickets must be zero when the launch starts: the last CTA of every epoch re-zeroes its own, but a workspace
+  // a C-ABI caller did not clear, or one an aborted launch left dirty, would silently corrupt the loss — 256 bytes per launch
+  if (cudaError_t e = cudaMemsetAsync(P.counters, 0, sizeof(unsigned int) * kMaxEpochs, st)) return int(e);
   kern<<<int(grid), SH::kThreads, smem, st>>>(P);
   return int(cudaGetLastError());
 }
@@ -2114,6 +2144,7 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
     return 0;
   }
   if (trace) fprintf(stderr, "[svbrdf] tile_kernel_ts mode %d tile %d slots %d smem %zu grid %lld\n", MODE, SH::kTile, slots, smem, grid);
+  if (cudaError_t e = cudaMemsetAsync(P.counters, 0, sizeof(unsigned int) * kMaxEpochs, st)) return int(e);
   kern<<<int(grid), SH::kThreads, smem, st>>>(P);
   return int(cudaGetLastError());
 }
@@ -2212,6 +2243,7 @@ size_t svbrdf_workspace_bytes(int32_t res, int32_t rows) {
 int svbrdf_render_fwd(const svbrdf_geom_t* geom, const float* tex, float* out, svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (!tex || !out) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.out = out;
@@ -2222,6 +2254,7 @@ int svbrdf_render_bwd(const svbrdf_geom_t* geom, const float* tex, const float* 
                       void* workspace, svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (!tex || !grad_out || !grad_tex || !workspace) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = grad_out;
@@ -2236,6 +2269,7 @@ int svbrdf_l2_grad(const svbrdf_geom_t* geom, const float* tex, const void* targ
                    float* grad_tex, float* loss_out, float* grad_pow, void* workspace, svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (!tex || !target || !grad_tex || !workspace || n_total < geom->n_lights) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = target;
@@ -2253,6 +2287,7 @@ int svbrdf_l2_adam_run(const svbrdf_geom_t* geom, float* tex, float* m, float* v
                        svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (!tex || !m || !v || !target || !adam || !workspace || epochs < 0 || adam->step < 1) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = tex;
   P.m = m;
@@ -2306,6 +2341,7 @@ int svbrdf_l2_grad_push(const svbrdf_geom_t* geom, const float* tex, const void*
   // bands x light shards, one peer group per band); ownership, receive slots and `tex` are all relative to the band
   if (!tex || !target || !workspace || n_total < geom->n_lights || geom->plane_stride != 0) return SVBRDF_E_BADARG;
   if ((long long)peers->world * peers->chunk < (long long)geom->rows * geom->res) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = target;
@@ -2333,6 +2369,7 @@ int svbrdf_reduce_adam_push(const svbrdf_peers_t* peers, int64_t texels, float* 
                             svbrdf_stream_t stream) {
   if (int e = check_peers(peers)) return e;
   if (!m || !v || !adam || adam->step < 1 || texels <= 0 || texels % 4 != 0) return SVBRDF_E_BADARG;
+  DeviceGuard guard(m);
   PushAdamParams Q{};
   Q.world = peers->world;
   Q.rank = peers->rank;
@@ -2357,6 +2394,7 @@ int svbrdf_render_norm_l2_fwd(const svbrdf_geom_t* geom, const float* tex, const
   if (int e = check_geom(geom)) return e;
   if (!tex || !out || !mean || !std_ || !workspace) return SVBRDF_E_BADARG;
   if (loss_out && !target) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.out = out;
@@ -2373,6 +2411,7 @@ int svbrdf_render_norm_l2_bwd(const svbrdf_geom_t* geom, const float* tex, const
                               svbrdf_stream_t stream) {
   if (int e = check_geom(geom)) return e;
   if (!tex || !grad_out || !grad_tex || !std_ || !workspace) return SVBRDF_E_BADARG;
+  DeviceGuard guard(tex);
   Params P = base_params(geom);
   P.tex = const_cast<float*>(tex);
   P.io = grad_out;
@@ -2391,6 +2430,7 @@ int svbrdf_adam_apply(float* param, float* m, float* v, const float* grad, size_
                       svbrdf_stream_t stream) {
   if (!param || !m || !v || !grad || !adam || adam->step < 1) return SVBRDF_E_BADARG;
   if (count == 0) return 0;
+  DeviceGuard guard(param);
   const AdamStep<float> a = make_adam(*adam, adam->step);
   const size_t want = (count / 4 + 255) / 256 + 1;
   const int blocks = int(want < size_t(148 * 16) ? want : size_t(148 * 16));

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "../../include/svbrdf_b200.h"
+#include "svbrdf_host.h"
 
 namespace svbrdf_maps {
 
@@ -243,6 +244,7 @@ extern "C" {
 int svbrdf_maps_encode_u8(const float* tex, int64_t plane_stride, int32_t rows, int32_t cols, int32_t clamp_input, uint8_t* bytes,
                           svbrdf_stream_t stream) {
   if (!tex || !bytes || rows <= 0 || cols <= 0) return SVBRDF_E_BADARG;
+  svbrdf::DeviceGuard guard(tex);
   const long long texels = (long long)rows * cols;
   const long long stride = plane_stride ? plane_stride : texels;
   if (stride < texels) return SVBRDF_E_BADARG;
@@ -254,6 +256,7 @@ int svbrdf_maps_encode_u8(const float* tex, int64_t plane_stride, int32_t rows, 
 
 int svbrdf_maps_decode_u8(const uint8_t* bytes, int32_t rows, int32_t cols, float* tex, int64_t plane_stride, svbrdf_stream_t stream) {
   if (!tex || !bytes || rows <= 0 || cols <= 0) return SVBRDF_E_BADARG;
+  svbrdf::DeviceGuard guard(tex);
   const long long texels = (long long)rows * cols;
   const long long stride = plane_stride ? plane_stride : texels;
   if (stride < texels) return SVBRDF_E_BADARG;
@@ -285,6 +288,7 @@ int svbrdf_resize_lanczos4_u8(const uint8_t* src, int32_t planes, int32_t src_ro
                               int32_t dst_cols, const int32_t* x_tap, const int16_t* x_coef, const int32_t* y_tap, const int16_t* y_coef,
                               svbrdf_stream_t stream) {
   if (!src || !dst || planes <= 0 || src_rows <= 0 || src_cols <= 0 || dst_rows <= 0 || dst_cols <= 0) return SVBRDF_E_BADARG;
+  svbrdf::DeviceGuard guard(src);
   if (src_rows == dst_rows && src_cols == dst_cols)      // cv::resize returns a copy
     return int(cudaMemcpyAsync(dst, src, size_t(planes) * src_rows * src_cols, cudaMemcpyDeviceToDevice, stream));
   if (!x_tap || !x_coef || !y_tap || !y_coef) return SVBRDF_E_BADARG;

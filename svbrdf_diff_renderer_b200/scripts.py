@@ -30,7 +30,11 @@ def render(json_dir, res):
     svbrdf_obj.save_images_th(rendereds, svbrdf_obj.target_dir)
 
 
-def optim_perpixel(json_dir, res, lr, epochs, tex_init, optim_light=False, uint8_targets=False):
+def optim_perpixel(json_dir, res, lr, epochs, tex_init, optim_light=False, uint8_targets="auto"):
+    """scripts.py:67-97.  ``uint8_targets``: ``"auto"`` (default) keeps the target PNGs as their bytes whenever they are 8-bit
+    RGB files (imageio.py:18-19 divides them by 255; the fused kernel does the same division, correctly rounded, so the
+    optimisation is bit-identical to the float32 route at a quarter of the upload and target traffic); ``False`` forces the
+    reference's float32 stack, ``True`` insists on bytes."""
     device = _device()
 
     svbrdf_obj = SvbrdfIO(json_dir, device)
@@ -66,7 +70,7 @@ def optim_perpixel(json_dir, res, lr, epochs, tex_init, optim_light=False, uint8
     return optim_obj
 
 
-def optim_perpixel_pyramid(stages, lr, epochs, tex_init="const", optim_light=False, uint8_targets=False):
+def optim_perpixel_pyramid(stages, lr, epochs, tex_init="const", optim_light=False, uint8_targets="auto"):
     """The reference's coarse-to-fine recipe (run.py:55-56: 256 -> 512 -> 1024, each stage initialised with the previous
     stage's maps) with the hand-off kept on the device.  ``stages`` is a list of ``(json_dir, res)``; every stage is
     one ``optim_perpixel`` call (same files written), stage k+1 starts from ``maps.handoff(stage k maps, res)`` — bit

@@ -45,6 +45,28 @@ def round_robin(n: int, world: int, rank: int):
     return list(range(rank, n, world))
 
 
+def bind_to_gpu_cpus(device_index: int):
+    """One process per GPU: restrict this process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA
+    node), so the pinned staging buffers it allocates afterwards — first touch by the allocating thread — live in the host
+    memory that GPU's PCIe root complex reaches without crossing the inter-socket link.  Returns the core list (``None`` when
+    NVML or the affinity call is unavailable: nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"cores": len(allowed), "first": allowed[0], "last": allowed[-1]}
+    except Exception:
+        return None
+
+
 def row_bands(res: int, bands: int):
     """Split the rows of a ``res x res`` image into ``bands`` contiguous bands (multiples of 8 rows when possible)."""
     bands = max(1, min(bands, res))

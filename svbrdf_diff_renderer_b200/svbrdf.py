@@ -248,7 +248,10 @@ class SvbrdfIO:
         if on_device:
             arrays = {k: imread_raw(textures_dir / f"{k}.png") for k in ("nom", "dif", "spe", "rgh")}
             eight_bit = all(a.dtype == np.uint8 for a in arrays.values())
-            if eight_bit and arrays["rgh"].ndim == 2 and all(arrays[k].ndim == 3 and arrays[k].shape[2] == 3 for k in ("nom", "dif", "spe")):
+            # the device path stacks the four maps into one [10,h,w] byte array: same source size required (the reference
+            # resizes each file on its own, so mixed-size map sets take the host path below, as they do there)
+            same_size = len({a.shape[:2] for a in arrays.values()}) == 1
+            if eight_bit and same_size and arrays["rgh"].ndim == 2 and all(arrays[k].ndim == 3 and arrays[k].shape[2] == 3 for k in ("nom", "dif", "spe")):
                 planes = maps.png_arrays_to_planes(arrays, self.device)
                 out = maps.decode_u8(maps.resize_lanczos4_u8(planes, res, res))
                 _log("[DONE:SvbrdfIO] Load textures (numbers in range [-1,1])")
@@ -282,19 +285,22 @@ class SvbrdfIO:
 
     def load_images_th(self, images_dir, res=256, as_uint8=False):
         """Targets as ``[N,3,res,res]``.  ``as_uint8=True`` keeps the decoded PNG bytes (the fused
-        kernel divides by 255 itself): a quarter of the HBM traffic of the float32 stack."""
+        kernel divides by 255 itself, bit-identical to the host's ``/255``): a quarter of the PCIe upload and of the HBM
+        traffic of the float32 stack.  ``as_uint8="auto"`` (what ``optim_perpixel`` passes): bytes when every file is an
+        8-bit 3-channel PNG — what ``save_images_th`` and the capture pipeline write — float32 otherwise."""
         if not images_dir.exists():
             raise FileNotFoundError(f"[ERROR:SvbrdfIO:load_images_th] {images_dir} is not exists")
-        stack = []
-        for idx in self.idx:
-            fn = images_dir / f"{idx:02d}.png"
-            if as_uint8:
-                im = imread_raw(fn, (res, res))
-                if im.dtype != np.uint8 or im.ndim != 3:
-                    raise ValueError(f"{fn}: as_uint8 needs an 8-bit 3-channel PNG")
-                stack.append(np.ascontiguousarray(im[:, :, ::-1].transpose(2, 0, 1)))
-            else:
-                stack.append(imread(fn, "srgb", (res, res)).transpose(2, 0, 1))
+        files = [images_dir / f"{idx:02d}.png" for idx in self.idx]
+        if as_uint8:
+            raw = [imread_raw(fn, (res, res)) for fn in files]
+            ok = all(im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3 for im in raw)
+            if ok:
+                _log("[DONE:SvbrdfIO] Load images (uint8)")
+                return self.np_to_th(np.stack([np.ascontiguousarray(im[:, :, ::-1].transpose(2, 0, 1)) for im in raw], 0))
+            if as_uint8 != "auto":
+                bad = next(fn for fn, im in zip(files, raw) if not (im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3))
+                raise ValueError(f"{bad}: as_uint8 needs an 8-bit 3-channel PNG")
+        stack = [imread(fn, "srgb", (res, res)).transpose(2, 0, 1) for fn in files]
         _log("[DONE:SvbrdfIO] Load images")
         return self.np_to_th(np.stack(stack, 0))
 
