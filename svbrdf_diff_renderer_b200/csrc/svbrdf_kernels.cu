@@ -123,7 +123,10 @@ constexpr int kStashFloats = 29;
 #define SV_STREAM_ONLY 0
 #endif
 
-enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3 };
+// kModeVjpL2: the consumer backward (svbrdf_render_norm_l2_bwd) on the TMA ring — per light chunk TWO ring slots arrive, the
+// upstream gradient of the normalised image (fp32) and the targets (fp32 / uint8), and the light body forms
+// grad/std + l2_grad * 2 (out - target)/n per sample in registers (LightMode kVjpL2).
+enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3, kModeVjpL2 = 4 };
 
 struct Params {
   // tile_kernel_ts: 2-D TMA descriptors {texel, plane} of the planar arrays (box = 160 texels x 9 planes)
@@ -752,14 +755,20 @@ __device__ __forceinline__ void mbar_wait_uniform(unsigned long long* bar, unsig
 // Chunk stream of one tile:  [tex] [lights 0..L-1] [lights L..2L-1] ... ([m] [v] in the fused mode), L = SH::kChunk.
 template <int MODE>
 __host__ __device__ __forceinline__ int chunks_per_tile(int n_lights, int chunk) {
-  return 1 + (n_lights + chunk - 1) / chunk + (MODE == kModeL2Adam ? 2 : 0);
+  return 1 + (n_lights + chunk - 1) / chunk * (MODE == kModeVjpL2 ? 2 : 1) + (MODE == kModeL2Adam ? 2 : 0);
 }
 
 template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
 __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
                                                unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4]) {
   typedef typename IoLoad<TGT>::elem elem;
-  constexpr int LM = (MODE == kModeVjp) ? kVjp : kL2;
+  constexpr int LM = (MODE == kModeVjp) ? kVjp : (MODE == kModeVjpL2 ? kVjpL2 : kL2);
+  float l2w = 0.f, stdv[3] = {1.f, 1.f, 1.f};
+  if (MODE == kModeVjpL2) {
+    l2w = __ldg(P.l2_up) * float(2.0 * P.loss_norm);        // d mse / d out = 2 (out - target) / n_elems, times the upstream scalar
+#pragma unroll
+    for (int c = 0; c < 3; ++c) stdv[c] = P.aff_std[c];
+  }
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = P.n_lights, S = P.slots;
   const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
@@ -853,8 +862,47 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     // ---- lights, SH::kChunk per ring slot ----
     for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
       float in[SH::kChunk][3];
+      float tg[MODE == kModeVjpL2 ? SH::kChunk : 1][3];
+      if constexpr (MODE == kModeVjpL2) {
+        // first slot of the chunk: the upstream gradient of the normalised image, d((x - mean)/std)/dx = 1/std applied here
+        // (IEEE division like the unfused torch route); lights past N were not loaded: their values are never used
+        wait_full();
+        const float* sg = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
+#pragma unroll
+        for (int j = 0; j < SH::kChunk; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? __fdiv_rn(sg[(j * 3 + c) * SH::kTile + tid], stdv[c]) : 0.f;
+        }
+        release(slot);
+        advance();
+      }
       wait_full();
       const elem* s = reinterpret_cast<const elem*>(ring + size_t(slot) * SH::kSlotBytes);
+      if constexpr (MODE == kModeVjpL2) {
+#pragma unroll
+        for (int j = 0; j < SH::kChunk; ++j) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tg[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
+        }
+        release(slot);
+        advance();
+        if (i0 + SH::kChunk <= N) {
+#pragma unroll
+          for (int j = 0; j < SH::kChunk; ++j) {
+            float o3[3];
+            shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g, tg[j], l2w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < SH::kChunk - 1; ++j) {
+            if (i0 + j < N) {
+              float o3[3];
+              shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g, tg[j], l2w);
+            }
+          }
+        }
+        continue;
+      }
       if (i0 + SH::kChunk <= N) {
         // full chunk: no per-light guards, so the three independent lights can be interleaved
 #pragma unroll
@@ -1292,7 +1340,13 @@ __device__ __forceinline__ void tile_producer(const Params& P, unsigned char* ri
     fill(tex_src, 4, 9);
     for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
       const int nl = min(SH::kChunk, N - i0);
-      fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
+      if (MODE == kModeVjpL2) {
+        // two slots per chunk: upstream gradient (always fp32), then the targets
+        fill(static_cast<const float*>(P.io) + size_t(i0) * 3 * P.stride, 4, 3 * nl);
+        fill(static_cast<const elem*>(P.io2) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
+      } else {
+        fill(static_cast<const elem*>(P.io) + size_t(i0) * 3 * P.stride, sizeof(elem), 3 * nl);
+      }
     }
     if (MODE == kModeL2Adam) {
       fill(P.m, 4, 9);
@@ -1767,7 +1821,7 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
     tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);    // whole warp, uniform control flow
   } else {
     if (SH::kPW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SH::kConsumerRegs));
-    if (SH::kLanes == 2) {
+    if constexpr (SH::kLanes == 2) {
       if (coloc) tile_consumer2<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
       else tile_consumer2<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
     } else {
@@ -2188,8 +2242,25 @@ static int launch_l2(const Params& P, bool want_pow, int tgt, cudaStream_t st) {
   return SVBRDF_E_UNSUPPORTED;
 }
 
+// The consumer backward with targets on the TMA ring (kModeVjpL2): needs what every tile launch needs (16-byte aligned
+// plane segments) for BOTH image-sized inputs.
+template <bool WANT_POW, int TGT>
+static int launch_vjp_l2_tile(const Params& P, cudaStream_t st) {
+  if (pick_chunk(P.n_lights) == 4) return launch_tile_shape<kModeVjpL2, WANT_POW, TGT, ScalarShape4>(P, st);
+  return launch_tile_shape<kModeVjpL2, WANT_POW, TGT, ScalarShape>(P, st);
+}
+
 template <bool BWD>
 static int launch_norm_l2(Params& P, bool want_pow, int tgt, cudaStream_t st) {
+  if (BWD && P.io2 && P.l2_up && !env_int("SVBRDF_B200_FORCE_LDG", 0) && (reinterpret_cast<uintptr_t>(P.io2) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(P.out) & 15) == 0) {
+    // one thread per texel with direct LDG ran at 24 % occupancy with 11.6 warps per issued instruction waiting on the
+    // long scoreboard (260 us at 1024^2 x 9, profiles/r02_modeb_kernels_1024x9_summary.txt): both streams go through the ring
+    if (tgt == SVBRDF_TARGET_U8 && tma_ok<SVBRDF_TARGET_U8>(P))
+      return want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_U8>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_U8>(P, st);
+    if (tgt == SVBRDF_TARGET_F32 && tma_ok<SVBRDF_TARGET_F32>(P))
+      return want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_F32>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_F32>(P, st);
+  }
   const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
   const int blocks = texel_blocks(P);
 #define SV_LAUNCH_NL2(WP, TG)                                                                                       \
