@@ -142,10 +142,13 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_run(res, lights, steps, warmup, budget_s=150.0):
-    """Times the reference's torch-CPU path (oracle/torch_port.py, op-for-op the reference's
-    Microfacet.eval + MSELoss + backward + torch.optim.Adam.step) on all host cores.  Each step
-    is a bounded sample of the workload: a band of `rows` full-width rows, all lights, sized after
-    a probe so the whole run fits `budget_s`."""
+    """Times the reference's torch-CPU path on all host cores.  With the reference's files staged (oracle/_ref, see
+    oracle/stage_ref.py — or the live tree in the build container) the step is the UNMODIFIED ``Microfacet.eval``
+    (src/microfacet.py:84-120) inside the loop body of ``SvbrdfOptim.optim`` (src/svbrdf.py:60-71: clamp -> eval -> MSELoss ->
+    backward -> torch.optim.Adam.step), kind "reference"; otherwise the op-for-op port (oracle/torch_port.py), kind "port".
+    Each step is a bounded sample of the workload: a top-left square crop of the image (the reference asserts square
+    textures), all lights, sized after a probe so the whole run fits ``budget_s``; per-pixel cost is uniform."""
+    from oracle import ref_loader
     from oracle import torch_port as tp
     from svbrdf_diff_renderer_b200 import synth
 
@@ -157,40 +160,56 @@ def cpu_reference_run(res, lights, steps, warmup, budget_s=150.0):
     th.set_num_threads(cores)
     cl = synth.calibration(lights)
     gt, t0 = synth.random_textures(res, 1), synth.random_textures(res, 2)
+    use_ref = ref_loader.available()
+    if use_ref:
+        with ref_loader.quiet():
+            RefMicrofacet, _, _ = ref_loader.load()
 
-    def make(rows):
-        band = (0, rows)
-        sc = tp.Scene(res, cl[0], cl[1], cl[2], synth.IM_SIZE_CM, th.float32, band)
+    def make(side):
+        """State for a side x side crop: renderer/scene, targets, parameter, optimiser."""
+        if use_ref:
+            with ref_loader.quiet():
+                ren = RefMicrofacet(res, lights, synth.IM_SIZE_CM, cl, "cpu")
+            ren.res = side                                   # plain attributes (microfacet.py:12-24): crop the pixel grid
+            for name in ("pos", "camera_pos", "light_pos", "light_pow"):
+                setattr(ren, name, getattr(ren, name)[:, :, :side, :side])
+            shade = ren.eval
+        else:
+            sc = tp.Scene(res, cl[0], cl[1], cl[2], synth.IM_SIZE_CM, th.float32, (0, side))
+            sc.plane, sc.cam, sc.light, sc.power = (a[:, :, :, :side] for a in (sc.plane, sc.cam, sc.light, sc.power))
+            shade = lambda t: tp.shade(sc, t)                # noqa: E731
         with th.no_grad():
-            tgt = tp.shade(sc, gt[:, :, :rows])
-        tex = t0[:, :, :rows].clone().requires_grad_(True)
+            tgt = shade(gt[:, :, :side, :side].contiguous())
+        tex = t0[:, :, :side, :side].clone().requires_grad_(True)
         opt = th.optim.Adam([tex], lr=LR, betas=(0.9, 0.999))
-        return sc, tgt, tex, opt
+        return shade, tgt, tex, opt, th.nn.MSELoss()
 
-    def step(sc, tgt, tex, opt):
-        loss = tp.l2_loss(tp.shade(sc, tex.clamp(-1, 1)), tgt)     # svbrdf.py:60-63
+    def step(shade, tgt, tex, opt, mse):
+        loss = mse(shade(tex.clamp(-1, 1)), tgt)             # svbrdf.py:60-63
         opt.zero_grad()
         loss.backward()
-        opt.step()                                                  # svbrdf.py:69-71
+        opt.step()                                           # svbrdf.py:69-71
         return loss
 
-    probe_rows = min(res, 64)
-    state = make(probe_rows)
+    probe = min(res, 256)
+    state = make(probe)
     step(*state)
     t = time.perf_counter()
     step(*state)
-    per_row = (time.perf_counter() - t) / probe_rows
-    rows = int(max(min(res, budget_s / max(steps + warmup, 1) / per_row), min(res, 32)))
-    state = make(rows)
+    per_px = (time.perf_counter() - t) / (probe * probe)
+    side = int(min(res, max(64, (budget_s / max(steps + warmup, 1) / per_px) ** 0.5)))
+    state = make(side)
     for _ in range(warmup):
         step(*state)
     t = time.perf_counter()
     for _ in range(steps):
         step(*state)
     dt = time.perf_counter() - t
-    samples = rows * res * lights
-    return {"value": samples * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} optim steps (after {warmup} warm-up) on a {rows}-row x {res}-col band of the {res}x{res}x{lights} workload, "
+    samples = side * side * lights
+    src = ("the unmodified reference Microfacet.eval (" + ("oracle/_ref staged copy" if ref_loader.staged() else "live reference tree") + ")") if use_ref \
+        else "oracle/torch_port.py (op-for-op port)"
+    return {"value": samples * steps / dt, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"{steps} optim steps (after {warmup} warm-up) on a {side}x{side} crop of the {res}x{res}x{lights} workload, {src}, "
                       f"torch {th.__version__} CPU fp32, {cores} threads",
             "ms_per_step_sample": dt / steps * 1e3, "iters_per_s_full_image": (samples * steps / dt) / (res * res * lights)}
 
@@ -206,8 +225,7 @@ def run_reference_arm(args):
         "ms_per_step": args.res * args.res * args.lights / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config_dict(args),
-        "reference_path": "oracle/torch_port.py (op-for-op restatement of the reference's torch path, pinned bit for bit to the unmodified "
-                          "reference by tests/test_oracle_pin.py; the reference itself is pure Python and does not travel to the GPU box)",
+        "reference_path": base["sample"],
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -41,7 +41,9 @@ enum {
 /* dtype of the target image stack handed to the L2 entry points */
 enum {
   SVBRDF_TARGET_F32 = 0, /* what SvbrdfIO.load_images_th returns (svbrdf.py:191-204) */
-  SVBRDF_TARGET_U8 = 1   /* the PNG bytes themselves; decoded as float(b)/255 in-kernel (imageio.py:18-19) */
+  SVBRDF_TARGET_U8 = 1,  /* the PNG bytes themselves; decoded as float(b)/255 in-kernel (imageio.py:18-19) */
+  SVBRDF_TARGET_F16 = 2  /* IEEE binary16 targets (half the bytes of f32; the conversion to float is exact); accepted by
+                            svbrdf_l2_grad, svbrdf_l2_grad_push, svbrdf_l2_adam_step/_run */
 };
 
 /* Capture geometry: the arguments of Microfacet.__init__ (microfacet.py:10-26). */

@@ -1,7 +1,7 @@
 """ORACLE helper (test infrastructure): import the UNMODIFIED reference classes.
 
-Works only where ``/root/reference`` exists (the build container; never on the
-GPU box).  ``src.optimization`` imports ``matplotlib.pyplot`` for its loss plot
+Uses ``/root/reference`` where it exists (the build container) and otherwise the byte-for-byte copy of the path's
+four files that ``oracle/stage_ref.py`` put into the git-ignored ``oracle/_ref/`` (that copy travels to the GPU box).  ``src.optimization`` imports ``matplotlib.pyplot`` for its loss plot
 (``/root/reference/src/optimization.py:7``), which is not installed here, so a
 stub module is injected first.  ``src.scripts`` is never imported (it pulls in
 ``pupil_apriltags`` and ``mitsuba``, both absent — SURVEY.md §8(c)).
@@ -16,10 +16,18 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("SVBRDF_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/stage_ref.py (travels to the GPU box)
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "microfacet.py")) and os.path.isfile(os.path.join(STAGED_ROOT, "src", "microfacet.py")):
+    REFERENCE_ROOT = STAGED_ROOT
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "microfacet.py"))
+
+
+def staged() -> bool:
+    """True when the classes come from the staged copy (``oracle/_ref``), i.e. not from the live reference tree."""
+    return REFERENCE_ROOT == STAGED_ROOT
 
 
 def load():

@@ -34,7 +34,7 @@ NVCC_FLAGS = [
     "-diag-suppress", "128",
 ]
 
-TARGET_F32, TARGET_U8 = 0, 1
+TARGET_F32, TARGET_U8, TARGET_F16 = 0, 1, 2
 
 EXPORTS = (
     "svbrdf_abi_version", "svbrdf_error_string", "svbrdf_workspace_bytes", "svbrdf_render_fwd", "svbrdf_render_bwd",
@@ -180,4 +180,6 @@ def target_dtype_code(t: th.Tensor) -> int:
         return TARGET_F32
     if t.dtype == th.uint8:
         return TARGET_U8
-    raise RuntimeError(f"targets: unsupported dtype {t.dtype} (float32 or uint8)")
+    if t.dtype == th.float16:
+        return TARGET_F16
+    raise RuntimeError(f"targets: unsupported dtype {t.dtype} (float32, float16 or uint8)")

@@ -27,6 +27,7 @@
 // every light is co-located with its camera is detected while staging; co-located captures
 // (everything the reference's capture code emits, capture.py:70-71) take the folded loop body.
 #include <cuda.h>              // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -234,6 +235,11 @@ template <>
 struct IoLoad<SVBRDF_TARGET_F32> {
   typedef float elem;
   static __device__ __forceinline__ float decode(float x) { return x; }
+};
+template <>
+struct IoLoad<SVBRDF_TARGET_F16> {
+  typedef __half elem;
+  static __device__ __forceinline__ float decode(__half x) { return __half2float(x); }   // exact
 };
 template <>
 struct IoLoad<SVBRDF_TARGET_U8> {
@@ -1057,6 +1063,13 @@ template <>
 struct IoLoad2<SVBRDF_TARGET_F32> {
   static __device__ __forceinline__ V2 at(const unsigned char* slot, int plane, int tile, int tid) {
     const float2 q = reinterpret_cast<const float2*>(slot + size_t(plane) * tile * 4)[tid];
+    return V2(q.x, q.y);
+  }
+};
+template <>
+struct IoLoad2<SVBRDF_TARGET_F16> {
+  static __device__ __forceinline__ V2 at(const unsigned char* slot, int plane, int tile, int tid) {
+    const float2 q = __half22float2(reinterpret_cast<const __half2*>(slot + size_t(plane) * tile * 2)[tid]);
     return V2(q.x, q.y);
   }
 };
@@ -2220,6 +2233,7 @@ static int launch_tile(Params P, cudaStream_t st) {
   // opt-in (SVBRDF_B200_TSTORE=1): measured 72.3 vs 71.2 us per epoch at 1024^2 x 9 and 1320 vs 1232 us at 2048^2 x 64 against the
   // per-thread-store kernel below, although it executes 8 % fewer instructions
 #if SV_ENABLE_TS
+  if constexpr (TGT != SVBRDF_TARGET_F16)                   // the store-back kernel's 2-D tensor maps cover f32 and u8 targets
   if (P.push_world == 0 && P.tile_rotate == 0 && out_ok && !env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT) && env_int("SVBRDF_B200_TSTORE", 0))
     return launch_tile_ts<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 #endif
@@ -2239,6 +2253,8 @@ static int launch_l2(const Params& P, bool want_pow, int tgt, cudaStream_t st) {
     return want_pow ? launch_tile<MODE, true, SVBRDF_TARGET_F32>(P, st) : launch_tile<MODE, false, SVBRDF_TARGET_F32>(P, st);
   if (tgt == SVBRDF_TARGET_U8)
     return want_pow ? launch_tile<MODE, true, SVBRDF_TARGET_U8>(P, st) : launch_tile<MODE, false, SVBRDF_TARGET_U8>(P, st);
+  if (tgt == SVBRDF_TARGET_F16)
+    return want_pow ? launch_tile<MODE, true, SVBRDF_TARGET_F16>(P, st) : launch_tile<MODE, false, SVBRDF_TARGET_F16>(P, st);
   return SVBRDF_E_UNSUPPORTED;
 }
 

@@ -52,13 +52,13 @@ class SvbrdfOptim(Optim):
         self.textures = self.gradient(th.cat((diffuse, normal, roughness, specular), 1))
 
     def load_targets(self, targets):
-        """``[N,3,R,R]`` float32 (what ``load_images_th`` returns) or uint8 (the PNG bytes)."""
-        if targets.dtype not in (th.float32, th.uint8):
+        """``[N,3,R,R]`` float32 (what ``load_images_th`` returns), uint8 (the PNG bytes) or float16."""
+        if targets.dtype not in (th.float32, th.uint8, th.float16):
             targets = targets.float()
         self.targets = targets.to(self.device).contiguous()
 
     def compute_image_loss(self, predicts):
-        tg = self.targets if self.targets.dtype == th.float32 else self.targets.float() / 255
+        tg = self.targets if self.targets.dtype == th.float32 else (self.targets.float() / 255 if self.targets.dtype == th.uint8 else self.targets.float())
         return self.loss_l2(predicts, tg)
 
     # ---- the loop (svbrdf.py:44-83) --------------------------------------------------------------
