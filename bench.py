@@ -562,10 +562,12 @@ def view_sharded_bench(args, dev, world, rank, barrier, res, n, dtype, label):
             nv.check(L.svbrdf_l2_adam_run(ctypes.byref(geom), nv.ptr(tex), nv.ptr(m), nv.ptr(v), nv.ptr(tgt), nv.target_dtype_code(tgt), ctypes.byref(a), k,
                                           nv.ptr(curve), None, nv.ptr(ws), nv.stream_ptr(dev)), "l2_adam_run")
         run(2, 1)
+        m.zero_()                                            # same protocol as the sharded optimisers below: every optim() call
+        v.zero_()                                            # starts Adam afresh on the maps the warm-up left behind
         th.cuda.synchronize()
         e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
         e0.record()
-        run(epochs, 3)
+        run(epochs, 1)
         e1.record()
         th.cuda.synchronize()
         ms = e0.elapsed_time(e1)
