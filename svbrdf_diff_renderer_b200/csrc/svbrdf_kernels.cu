@@ -104,6 +104,32 @@ struct TileShape {
 typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 3, SV_PRODUCER_WARPS, SV_CONSUMER_REGS> ScalarShape;
 typedef TileShape<SV_CONSUMER_WARPS, 1, SV_TILE_MAXNREG, 4, SV_PRODUCER_WARPS, SV_CONSUMER_REGS> ScalarShape4;
 typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG, 3> PackedShape;
+// Self-fed ring (PW = 0): NO producer warp.  16 consumer warps x 128 registers fill the register file and put the same
+// number of warps (4) on each of the SM's 4 sub-partitions — with 15 + 1 three sub-partitions carry 4/15 of the texels each
+// and the fourth 3/15 plus the producer's polling.  The ring is refilled by whichever consumer warp hands a slot back LAST:
+// mbarrier.arrive returns the barrier state before the arrival, mbarrier.pending_count == 1 identifies the last of the 16
+// arrivals, and that warp (in uniform control flow, one elected lane issuing) streams the chunk NS positions further
+// down the CTA's chunk stream into the slot before it waits for its own next chunk.  Nobody polls an `empty` barrier.
+#ifndef SV_SELF_WARPS
+#define SV_SELF_WARPS 16
+#endif
+typedef TileShape<SV_SELF_WARPS, 1, SV_TILE_MAXNREG, 3, 0> SelfShape;
+typedef TileShape<SV_SELF_WARPS, 1, SV_TILE_MAXNREG, 4, 0> SelfShape4;
+// Measured (profiles/r02_selffed_ring.md): correct (all GPU tests pass through it) and perfectly balanced — every scheduler
+// issues on 63-68 % of its cycles — but 19 % SLOWER than 15 + 1 (5.35 vs 4.49 ms at 4096^2 x 64, 86.3 vs 70.7 us at 1024^2 x 9):
+// the refill lands on the critical path of the slowest warp, which therefore stays the slowest and ends up doing all of
+// them, and the hand-back bookkeeping costs every warp ~20 instructions per slot — as many as the producer warp's polling
+// wasted.  Compiled only with -DSV_ENABLE_SELF=1 and selected with SVBRDF_B200_SELFFED=1.
+#ifndef SV_ENABLE_SELF
+#define SV_ENABLE_SELF 0
+#endif
+#ifndef SV_SELFFED_DEFAULT
+#define SV_SELFFED_DEFAULT 0
+#endif
+// SV_SELF_EAGER: the last warp to hand a slot back refills it right there (1) instead of before its next wait (0)
+#ifndef SV_SELF_EAGER
+#define SV_SELF_EAGER 1
+#endif
 // SV_STASH: park the values only the epilogue needs (raw texel, gamma derivatives, normal reconstruction:
 // 29 floats per texel) in shared memory while the light loop runs, instead of in registers: the compiler
 // then stops rematerialising per-texel constants inside the loop.  Measured (profiles/r01_variants.txt):
@@ -111,7 +137,7 @@ typedef TileShape<SV_PACKED_WARPS, 2, SV_PACKED_MAXNREG, 3> PackedShape;
 #ifndef SV_STASH
 #define SV_STASH 1
 #endif
-constexpr int kStashFloats = 29;
+constexpr int kStashFloats = 28;          // raw[9] dpow[7] d[3] oms[3] rough alpha mx my mz rlen
 // SV_PAIR_CHANNELS: inside one texel, independent channels (RGB radiance chain, the 7 gamma-encoded texture channels,
 // the 9 Adam updates) are processed two at a time with the packed FP32x2 instructions — no extra registers, fewer
 // issue slots for the same FMA-pipe work (the scalar kernel is issue-bound).
@@ -694,6 +720,31 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive and report whether this arrival was the last one of the phase (the state returned by mbarrier.arrive is the one
+// BEFORE the arrival: one pending arrival left = ours).  SV_SELF_LAST is the pending count that identifies it.
+#ifndef SV_SELF_LAST
+#define SV_SELF_LAST 1
+#endif
+// Lane 0 arrives (predicated, no divergent branch); the other lanes get 0.
+__device__ __forceinline__ unsigned mbar_arrive_is_last(unsigned long long* bar, int lane) {
+  unsigned last;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 st;\n"
+      ".reg .u32 c;\n"
+      "setp.eq.u32 p, %1, 0;\n"
+      "mov.u32 c, 0;\n"
+      "@p mbarrier.arrive.shared::cta.b64 st, [%2];\n"
+      "@p mbarrier.pending_count.b64 c, st;\n"
+      "setp.eq.u32 q, c, %3;\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(last)
+      : "r"(lane), "r"(smem_u32(bar)), "n"(SV_SELF_LAST)
+      : "memory");
+  return last;
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
   asm volatile(
@@ -764,9 +815,69 @@ __host__ __device__ __forceinline__ int chunks_per_tile(int n_lights, int chunk)
   return 1 + (n_lights + chunk - 1) / chunk * (MODE == kModeVjpL2 ? 2 : 1) + (MODE == kModeL2Adam ? 2 : 0);
 }
 
+// Self-fed ring: stream chunk number `chunk` of this CTA's chunk stream (epochs x tiles x chunks_per_tile, the order the
+// consumers walk it) into ring slot `slot`.  Executed by a whole warp in uniform control flow; one elected lane issues.
+// Cross-epoch hazard (the texture / m / v planes of a tile were stored by this CTA one epoch earlier): every consumer warp
+// fences its stores (publish_tiles) at least every `publish_every` tiles, and a chunk is only requested once ALL warps have
+// handed back the chunk `slots` positions ahead of it — with >= 4 tiles per CTA (the launcher's condition for multi-epoch
+// self-fed launches) that hand-back is later than the fence of the tile in question for every warp.
+// The refill sits on the critical path of the slowest warp (it is the last to hand a slot back), so it has to be short:
+// a chunk moves as kTile/256 two-dimensional TMA boxes ([planes][256 texels] through a tensor map of the planar array) —
+// two instructions instead of 9-12 one-plane bulk copies (a first version with those spent ~2300 cycles per refill in the
+// warp everybody else was waiting for: 7.08 instead of 4.48 ms at 4096^2 x 64) — and the chunk index is split into
+// (epoch, tile, stage) with multiply-high by precomputed reciprocals.  Texels past the end of the array and planes past
+// the last light are zero-filled by the TMA unit and count towards the transaction bytes, so every chunk of a kind has
+// the same size.  Its constants live in shared memory (filled once per CTA), so the light loop carries no extra registers
+// for it; not inlined — it runs once per slot per CTA, from eight call sites in the consumer.
+constexpr int kSelfBoxW = 256;                             // texels per TMA box (the box-dimension limit)
+struct SelfFeed {
+  const CUtensorMap* tm_tex; const CUtensorMap* tm_io; const CUtensorMap* tm_m; const CUtensorMap* tm_v;
+  long long lo;                                            // first texel of the CTA's first tile
+  long long tile_step;                                     // texels from one of the CTA's tiles to the next
+  unsigned ring, full;                                     // shared-memory addresses of the ring and of full[0]
+  unsigned my_tiles, cpt, rcp_tiles, rcp_cpt;              // rcp_x = ceil(2^32 / x): n / x = umulhi(n, rcp_x) for n x < 2^32
+  int n_light_chunks, epochs;
+};
+template <int MODE, int TGT, typename SH>
+__device__ __noinline__ void self_fill(const SelfFeed* __restrict__ fp, unsigned chunk, unsigned slot) {
+  const SelfFeed f = *fp;                                  // shared memory: the consumers keep none of this in registers
+  typedef typename IoLoad<TGT>::elem elem;
+  static_assert(MODE != kModeVjpL2, "the self-fed ring streams one slot per light chunk");
+  static_assert(SH::kTile % kSelfBoxW == 0, "whole boxes per tile");
+  const unsigned tile_idx = f.cpt == 1u ? chunk : __umulhi(chunk, f.rcp_cpt);          // running tile index over the epochs of this launch
+  const unsigned stage = chunk - tile_idx * f.cpt;         // 0: textures, 1..: light chunks, then m, v
+  const unsigned e = f.my_tiles == 1u ? tile_idx : __umulhi(tile_idx, f.rcp_tiles);
+  if (e >= unsigned(f.epochs)) return;                     // past the end of the stream
+  const unsigned local = tile_idx - e * f.my_tiles;
+  const int x0 = int(f.lo + (long long)local * f.tile_step);
+  const CUtensorMap* tm = f.tm_tex;
+  int y0 = 0;
+  unsigned box_bytes = 9u * kSelfBoxW * 4u;
+  if (stage != 0u) {
+    if (int(stage) <= f.n_light_chunks) {
+      tm = f.tm_io;
+      y0 = (int(stage) - 1) * SH::kChunk * 3;
+      box_bytes = 3u * SH::kChunk * kSelfBoxW * unsigned(sizeof(elem));
+    } else {
+      tm = int(stage) == f.n_light_chunks + 1 ? f.tm_m : f.tm_v;
+    }
+  }
+  const unsigned dst = f.ring + slot * unsigned(SH::kSlotBytes);
+  const unsigned bar = f.full + slot * 8u;
+  if (elect_one()) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(box_bytes * unsigned(SH::kTile / kSelfBoxW)) : "memory");
+#pragma unroll
+    for (int q = 0; q < SH::kTile / kSelfBoxW; ++q)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst + q * box_bytes),
+                   "l"(reinterpret_cast<unsigned long long>(tm)), "r"(x0 + q * kSelfBoxW), "r"(y0), "r"(bar)
+                   : "memory");
+  }
+}
+
 template <int MODE, bool COLOC, bool WANT_POW, int TGT, typename SH>
 __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __restrict__ s_geo, unsigned char* ring,
-                                               unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4]) {
+                                               unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4],
+                                               SelfFeed* sfeed = nullptr) {
   typedef typename IoLoad<TGT>::elem elem;
   constexpr int LM = (MODE == kModeVjp) ? kVjp : (MODE == kModeVjpL2 ? kVjpL2 : kL2);
   float l2w = 0.f, stdv[3] = {1.f, 1.f, 1.f};
@@ -794,13 +905,77 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
   auto wait_full = [&]() { if (!ready) mbar_wait(&full[slot], phase); };
 #else
   auto advance = [&]() { ++it; if (++slot == unsigned(S)) { slot = 0; phase ^= 1; } };
-  auto wait_full = [&]() { mbar_wait(&full[slot], phase); };
 #endif
-  auto release = [&](unsigned s) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[s]); };
-
   // multi-epoch launches: progress is published (with a fence) a few times per epoch, not per tile
   const TileMap tmap = tile_map<SH::kTile>(P, P.span, n_tiles);
   const unsigned my_tiles = tmap.count;
+  constexpr bool kSelf = SH::kPW == 0;                     // self-fed ring: no producer warp (see SelfShape)
+  // Where this thread's value of plane k sits in a ring slot.  Producer-fed ring: planes of kTile texels back to back.
+  // Self-fed ring: a chunk arrives as kTile/256 two-dimensional TMA boxes of [planes][256 texels], one after the other.
+  constexpr int kPS = kSelf ? kSelfBoxW : SH::kTile;       // plane stride (elements)
+  const int tix9 = kSelf ? (tid / kSelfBoxW) * (9 * kSelfBoxW) + (tid % kSelfBoxW) : tid;                  // texture / m / v chunks
+  const int tixL = kSelf ? (tid / kSelfBoxW) * (3 * SH::kChunk * kSelfBoxW) + (tid % kSelfBoxW) : tid;     // light chunks
+  const unsigned cpt = unsigned(chunks_per_tile<MODE>(N, SH::kChunk));
+  unsigned was_last = 0;                                   // lane 0: our hand-back of the previous chunk's slot completed its phase
+  if constexpr (kSelf) {
+    if (tid == 0) {                                        // the refill's constants (read by self_fill only)
+      SelfFeed f;
+      f.tm_tex = &P.tm_tex; f.tm_io = &P.tm_io; f.tm_m = &P.tm_m; f.tm_v = &P.tm_v;
+      f.lo = tile_first<SH::kTile>(tmap, P, 0u, n_tiles);
+      f.tile_step = tmap.spans ? (long long)SH::kTile : (long long)SH::kTile * gridDim.x;
+      f.ring = smem_u32(ring); f.full = smem_u32(full);
+      f.my_tiles = my_tiles; f.cpt = cpt;
+      f.rcp_cpt = cpt > 1u ? unsigned(((1ull << 32) + cpt - 1u) / cpt) : 0u;
+      f.rcp_tiles = my_tiles > 1u ? unsigned(((1ull << 32) + my_tiles - 1u) / my_tiles) : 0u;
+      f.n_light_chunks = (N + SH::kChunk - 1) / SH::kChunk; f.epochs = P.epochs;
+      *sfeed = f;
+      __threadfence_block();
+    }
+    __syncwarp();                                          // warp 0 primes the ring below: lane 0's stores first
+  }
+  if constexpr (kSelf) {
+    if (tid < 32 && my_tiles > 0u) {                       // warp 0 primes the ring: chunks 0 .. S-1
+      for (unsigned c = 0; c < unsigned(S); ++c) self_fill<MODE, TGT, SH>(sfeed, c, c);
+    }
+  }
+  // before waiting for chunk `it`: if this warp was the last of the CTA to hand back chunk it-1, its slot is free —
+  // refill it with chunk it-1+S (the try_wait on the completed phase is the acquire side of the other warps' arrivals)
+  auto service = [&]() {
+    if constexpr (kSelf) {
+      if (__any_sync(0xffffffffu, was_last != 0u)) {
+        was_last = 0u;
+        const unsigned ps = slot == 0u ? unsigned(S) - 1u : slot - 1u;
+        mbar_wait_uniform(&empty[ps], slot == 0u ? phase ^ 1u : phase);
+        self_fill<MODE, TGT, SH>(sfeed, it - 1u + unsigned(S), ps);
+      }
+    }
+  };
+#if !SV_PROBE_AHEAD
+  auto wait_full = [&]() {
+#if !SV_SELF_EAGER
+    if constexpr (kSelf) service();
+#endif
+    mbar_wait(&full[slot], phase);
+  };
+#endif
+  auto release = [&](unsigned s) {
+    __syncwarp();
+    if constexpr (kSelf) {
+      was_last = mbar_arrive_is_last(&empty[s], lane);
+#if SV_SELF_EAGER
+      // refill at once (the round trip of the arrival overlaps the LDS latency the warp is about to wait for anyway):
+      // chunk `it` was just handed back, chunk it + S goes into its slot
+      if (__any_sync(0xffffffffu, was_last != 0u)) {
+        mbar_wait_uniform(&empty[s], phase);
+        self_fill<MODE, TGT, SH>(sfeed, it + unsigned(S), s);
+      }
+      was_last = 0u;
+#endif
+    } else {
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  };
+
   const unsigned publish_every = my_tiles >= 6 ? my_tiles / 3 : 1;
   unsigned tiles_finished = 0;
   for (int e = 0; e < P.epochs; ++e) {
@@ -821,7 +996,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
     {
       const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) raw[k] = s[k * SH::kTile + tid];
+      for (int k = 0; k < 9; ++k) raw[k] = s[k * kPS + tix9];
     }
     release(slot);
     advance();
@@ -877,7 +1052,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
         for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? __fdiv_rn(sg[(j * 3 + c) * SH::kTile + tid], stdv[c]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? __fdiv_rn(sg[(j * 3 + c) * kPS + tixL], stdv[c]) : 0.f;
         }
         release(slot);
         advance();
@@ -888,7 +1063,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
         for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) tg[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
+          for (int c = 0; c < 3; ++c) tg[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kPS + tixL]) : 0.f;
         }
         release(slot);
         advance();
@@ -914,7 +1089,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
         for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]);
+          for (int c = 0; c < 3; ++c) in[j][c] = IoLoad<TGT>::decode(s[(j * 3 + c) * kPS + tixL]);
         }
         release(slot);
         advance();
@@ -932,7 +1107,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #pragma unroll
         for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * SH::kTile + tid]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? IoLoad<TGT>::decode(s[(j * 3 + c) * kPS + tixL]) : 0.f;
         }
         release(slot);
         advance();
@@ -977,7 +1152,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) mk[k] = s[k * SH::kTile + tid];
+        for (int k = 0; k < 9; ++k) mk[k] = s[k * kPS + tix9];
       }
       release(slot);
       advance();
@@ -985,7 +1160,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       {
         const float* s = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) vk[k] = s[k * SH::kTile + tid];
+        for (int k = 0; k < 9; ++k) vk[k] = s[k * kPS + tix9];
       }
       release(slot);
       advance();
@@ -1826,12 +2001,14 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
   }
   const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
 
-  if (tid >= SH::kConsumers) {
+  bool producer = false;
+  if constexpr (SH::kPW > 0) producer = tid >= SH::kConsumers;     // PW = 0: self-fed ring, every warp is a consumer
+  if (producer) {
     if (SH::kPW == 4) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
       if (tid >= SH::kConsumers + 32) return;                      // only the first warp of the producer warpgroup works
     }
-    tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);    // whole warp, uniform control flow
+    if constexpr (SH::kPW > 0) tile_producer<MODE, TGT, SH>(P, ring, full, empty, s_done);    // whole warp, uniform control flow
   } else {
     if (SH::kPW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SH::kConsumerRegs));
     if constexpr (SH::kLanes == 2) {
@@ -1842,6 +2019,35 @@ __global__ void __maxnreg__(SH::kMaxReg) tile_kernel(const Params P) {
       else tile_consumer<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red);
     }
   }
+}
+
+// Self-fed shapes (PW = 0): every warp is a consumer.  Params is __grid_constant__ so that the tensor maps inside it can be
+// addressed in place (cp.async.bulk.tensor takes a generic pointer to the descriptor).
+template <int MODE, bool WANT_POW, int TGT, typename SH>
+__global__ void __maxnreg__(SH::kMaxReg) tile_kernel_self(const __grid_constant__ Params P) {
+  static_assert(SH::kPW == 0 && SH::kLanes == 1, "self-fed scalar shape");
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* ring = smem;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + size_t(P.slots) * SH::kSlotBytes);
+  unsigned long long* empty = full + P.slots;
+  float4* s_geo = reinterpret_cast<float4*>(empty + P.slots);
+  float* stash = reinterpret_cast<float*>(s_geo + 2 * P.n_lights);
+  __shared__ unsigned s_done[SH::kCW];
+  __shared__ float s_red[2][SH::kCW][4];
+  __shared__ SelfFeed s_feed;
+  const int tid = threadIdx.x;
+  if (tid < SH::kCW) s_done[tid] = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < P.slots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], SH::kCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  const bool coloc = stage_lights(P, s_geo, tid, SH::kThreads);     // includes __syncthreads
+  if (coloc) tile_consumer<MODE, true, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red, &s_feed);
+  else tile_consumer<MODE, false, WANT_POW, TGT, SH>(P, s_geo, ring, full, empty, stash, s_done, s_red, &s_feed);
 }
 
 // View-sharded push mode, second half: owner-side reduction of the `world` partial gradients (fixed rank order),
@@ -2149,17 +2355,90 @@ static TensorMapEncodeFn tensor_map_encoder() {
   }();
   return fn;
 }
-static bool make_plane_map(CUtensorMap* tm, const void* base, bool u8, long long texels, long long planes, long long stride_elems) {
+static bool make_plane_map(CUtensorMap* tm, const void* base, int elem_bytes, long long texels, long long planes, long long stride_elems,
+                           int box_w = kBoxW, int box_h = 9) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc || !base) return false;
-  const cuuint64_t eb = u8 ? 1 : 4;
+  const cuuint64_t eb = cuuint64_t(elem_bytes);             // 1 = uint8, 2 = float16, 4 = float32
+  const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   const cuuint64_t dims[2] = {cuuint64_t(texels), cuuint64_t(planes)};
   const cuuint64_t strides[1] = {cuuint64_t(stride_elems) * eb};
-  const cuuint32_t box[2] = {cuuint32_t(kBoxW), 9u};
+  const cuuint32_t box[2] = {cuuint32_t(box_w), cuuint32_t(box_h)};
   const cuuint32_t estr[2] = {1u, 1u};
-  return enc(tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+  return enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Self-fed ring (SelfShape): 16 consumer warps, no producer warp, chunks loaded as 2-D TMA boxes through tensor maps of the
+// planar arrays.  `FB` is the producer-fed shape to fall back to when the maps cannot be built (>= 2^31 texels, no driver
+// entry point) or the ring would be too shallow.
+template <int MODE, bool WANT_POW, int TGT, typename SH, typename FB>
+static int launch_tile_self(Params P, cudaStream_t st) {
+  const bool trace = env_int("SVBRDF_B200_TRACE", 0) != 0;
+  Device d;
+  if (int e = device_info(&d)) return e;
+  const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
+  const size_t stash_bytes = SV_STASH ? size_t(kStashFloats) * SH::kTile * 4 : 0;
+  const size_t fixed = geo + stash_bytes + 64 + 2 * 8 * 64;
+  const size_t static_smem = 1024;
+  const size_t budget = size_t(d.smem_optin + 1024) - 1024 - static_smem;
+  int slots = env_int("SVBRDF_B200_SLOTS", 0);
+  if (slots <= 0) slots = int((budget - fixed) / SH::kSlotBytes);
+  const int need = chunks_per_tile<MODE>(P.n_lights, SH::kChunk);
+  if (slots > 2 * need) slots = 2 * need;
+  if (slots > 64) slots = 64;
+  const size_t smem = size_t(slots) * SH::kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
+  if (slots < 3 || smem + static_smem > size_t(d.smem_optin)) return launch_tile_shape<MODE, WANT_POW, TGT, FB>(P, st);
+  P.slots = slots;
+  {
+    bool ok = P.texels < (1ll << 31) - SH::kTile &&
+              make_plane_map(&P.tm_tex, P.tex, 4, P.texels, 9, P.stride, kSelfBoxW, 9) &&
+              make_plane_map(&P.tm_io, P.io, int(sizeof(typename IoLoad<TGT>::elem)), P.texels, 3ll * P.n_lights, P.stride, kSelfBoxW, 3 * SH::kChunk);
+    if (MODE == kModeL2Adam)
+      ok = ok && make_plane_map(&P.tm_m, P.m, 4, P.texels, 9, P.stride, kSelfBoxW, 9) &&
+           make_plane_map(&P.tm_v, P.v, 4, P.texels, 9, P.stride, kSelfBoxW, 9);
+    if (!ok) return launch_tile_shape<MODE, WANT_POW, TGT, FB>(P, st);
+  }
+  auto kern = tile_kernel_self<MODE, WANT_POW, TGT, SH>;
+  static int smem_set[64] = {0};
+  if (int e = set_smem_once(reinterpret_cast<const void*>(kern), d.index, smem, smem_set)) return e;
+  const long long n_tiles = (P.texels + SH::kTile - 1) / SH::kTile;
+  long long grid = d.sms;
+  if (grid > n_tiles) grid = n_tiles;
+  P.span = 0;
+  if (n_tiles >= 8 * grid && env_int("SVBRDF_B200_SPANS", 1)) {          // equal load per CTA, as in launch_tile_shape
+    long long span = (P.texels + d.sms - 1) / d.sms;
+    span = (span + 31) / 32 * 32;
+    if (span < 32 * 4) span = 32 * 4;
+    P.span = span;
+    grid = (P.texels + span - 1) / span;
+  }
+  long long tiles_per_cta = n_tiles / grid;
+  if (P.span) {
+    const long long last = P.texels - (grid - 1) * P.span;
+    tiles_per_cta = (last + SH::kTile - 1) / SH::kTile;
+    if (grid > 1 && (P.span + SH::kTile - 1) / SH::kTile < tiles_per_cta) tiles_per_cta = (P.span + SH::kTile - 1) / SH::kTile;
+  }
+  P.counters = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
+  if (grid > kRowsPerEpoch) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  // multi-epoch launches need >= 4 tiles per CTA: a tile's reload is requested when the chunk `slots` positions ahead of
+  // it (<= 2 tiles) has been handed back by every warp, and every warp must have fenced the tile's stores before that
+  if (P.epochs > 1 && tiles_per_cta < 4) {
+    Params Q = P;
+    for (int e = 0; e < P.epochs; ++e) {
+      Q.epochs = 1;
+      Q.step_size[0] = P.step_size[e];
+      Q.inv_sqrt_bc2[0] = P.inv_sqrt_bc2[e];
+      Q.loss_out = P.loss_out ? P.loss_out + e : nullptr;
+      if (int err = launch_tile_self<MODE, WANT_POW, TGT, SH, FB>(Q, st)) return err;
+    }
+    return 0;
+  }
+  if (trace) fprintf(stderr, "[svbrdf] tile_kernel_self mode %d tile %d slots %d smem %zu grid %lld\n", MODE, SH::kTile, slots, smem, grid);
+  if (cudaError_t e = cudaMemsetAsync(P.counters, 0, sizeof(unsigned int) * kMaxEpochs, st)) return int(e);
+  kern<<<int(grid), SH::kThreads, smem, st>>>(P);
+  return int(cudaGetLastError());
 }
 
 // tile_kernel_ts (results written back by TMA): scalar shape, local outputs only (the peer-push mode keeps per-thread
@@ -2185,10 +2464,10 @@ static int launch_tile_ts(Params P, cudaStream_t st) {
   if (smem + static_smem > size_t(d.smem_optin)) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
   {
     const bool u8 = TGT == SVBRDF_TARGET_U8;
-    bool ok = P.texels < (1ll << 31) && make_plane_map(&P.tm_tex, P.tex, false, P.texels, 9, P.stride) &&
-              make_plane_map(&P.tm_io, P.io, u8, P.texels, 3ll * P.n_lights, P.stride);
-    if (MODE == kModeL2Adam) ok = ok && make_plane_map(&P.tm_m, P.m, false, P.texels, 9, P.stride) && make_plane_map(&P.tm_v, P.v, false, P.texels, 9, P.stride);
-    else ok = ok && make_plane_map(&P.tm_out, P.out, false, P.texels, 9, P.stride);
+    bool ok = P.texels < (1ll << 31) && make_plane_map(&P.tm_tex, P.tex, 4, P.texels, 9, P.stride) &&
+              make_plane_map(&P.tm_io, P.io, u8 ? 1 : 4, P.texels, 3ll * P.n_lights, P.stride);
+    if (MODE == kModeL2Adam) ok = ok && make_plane_map(&P.tm_m, P.m, 4, P.texels, 9, P.stride) && make_plane_map(&P.tm_v, P.v, 4, P.texels, 9, P.stride);
+    else ok = ok && make_plane_map(&P.tm_out, P.out, 4, P.texels, 9, P.stride);
     if (!ok) return launch_tile_shape<MODE, WANT_POW, TGT, SH>(P, st);
   }
   auto kern = tile_kernel_ts<MODE, WANT_POW, TGT, SH>;
@@ -2243,6 +2522,13 @@ static int launch_tile(Params P, cudaStream_t st) {
   if (P.push_world == 0 && env_int("SVBRDF_B200_PACKED", SV_PACKED_DEFAULT)) return launch_tile_shape<MODE, WANT_POW, TGT, PackedShape>(P, st);
 #endif
   static_assert(ScalarShape4::kTile == ScalarShape::kTile, "peer ownership granularity is one tile of either scalar shape");
+  // self-fed ring (16 consumer warps, no producer warp): not for the peer-sharded modes (480-texel ownership granularity)
+#if SV_ENABLE_SELF
+  if (P.push_world == 0 && P.tile_rotate == 0 && env_int("SVBRDF_B200_SELFFED", SV_SELFFED_DEFAULT)) {
+    if (pick_chunk(P.n_lights) == 4) return launch_tile_self<MODE, WANT_POW, TGT, SelfShape4, ScalarShape4>(P, st);
+    return launch_tile_self<MODE, WANT_POW, TGT, SelfShape, ScalarShape>(P, st);
+  }
+#endif
   if (pick_chunk(P.n_lights) == 4) return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape4>(P, st);
   return launch_tile_shape<MODE, WANT_POW, TGT, ScalarShape>(P, st);
 }
