@@ -153,7 +153,9 @@ constexpr int kStashFloats = 28;          // raw[9] dpow[7] d[3] oms[3] rough al
 // kModeVjpL2: the consumer backward (svbrdf_render_norm_l2_bwd) on the TMA ring — per light chunk TWO ring slots arrive, the
 // upstream gradient of the normalised image (fp32) and the targets (fp32 / uint8), and the light body forms
 // grad/std + l2_grad * 2 (out - target)/n per sample in registers (LightMode kVjpL2).
-enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3, kModeVjpL2 = 4 };
+// kModeNormFwd: the consumer forward (svbrdf_render_norm_l2_fwd) on the ring — the targets stream through the slots, each
+// light is rendered, compared with its target (L2 partial sums) and stored normalised; no backward half, no epilogue.
+enum KernelMode { kModeRender = 0, kModeVjp = 1, kModeL2Grad = 2, kModeL2Adam = 3, kModeVjpL2 = 4, kModeNormFwd = 5 };
 
 struct Params {
   // tile_kernel_ts: 2-D TMA descriptors {texel, plane} of the planar arrays (box = 160 texels x 9 planes)
@@ -604,6 +606,37 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
 // normalised image, adds the L2 term's gradient from the target and chains to the textures (instead of 4 image-sized
 // passes + the render VJP).  One thread per texel, direct LDG/STG.
 // ---------------------------------------------------------------------------------------------
+// x / b with IEEE rounding for a divisor that is fixed for the whole launch (the per-channel std of Normalize): the
+// correctly rounded reciprocal r = RN(1/b) is formed once, then q0 = RN(x r), rem = x - q0 b (exact in an FMA),
+// q = RN(q0 + rem r) is the correctly rounded quotient (Markstein) — three FMA-pipe instructions instead of the ~10 plus a
+// MUFU.RCP of the general division.  Checked against IEEE division with exact rational arithmetic for 196 000 (x, b)
+// pairs incl. all-ones significands; tests/test_gpu_features.py compares the normalised image with torch bit for bit.
+// Launches whose divisors lie outside [1e-30, 1e30] (reciprocal or quotient could leave the normal range) keep the
+// general division (norm_l2_kernel).
+struct FixedDiv {
+  float b, r;
+};
+__device__ __forceinline__ FixedDiv make_fixed_div(float b) {
+  FixedDiv d;
+  d.b = b;
+  d.r = __fdiv_rn(1.f, b);
+  return d;
+}
+__device__ __forceinline__ float div_rn(float x, const FixedDiv& d) {
+  const float q0 = __fmul_rn(x, d.r);
+  const float rem = __fmaf_rn(-q0, d.b, x);
+  return __fmaf_rn(rem, d.r, q0);
+}
+// the launcher's side of the contract: every divisor and every mean inside the range where neither r nor q can leave the
+// normal range for a rendered value in [0, 1]
+static bool fixed_div_ok(const float* mean, const float* std_) {
+  for (int c = 0; c < 3; ++c) {
+    const float a = fabsf(std_[c]);
+    if (!(a > 1e-30f && a < 1e30f) || !(fabsf(mean[c]) < 1e30f)) return false;
+  }
+  return true;
+}
+
 template <bool BWD, bool COLOC, bool WANT_POW, int TGT>
 __device__ __forceinline__ void norm_l2_lights(const Params& P, const float4* __restrict__ s_geo, const Texel<float>& tx, long long p, bool valid,
                                                 Grads<float>& g) {
@@ -879,8 +912,14 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
                                                unsigned long long* full, unsigned long long* empty, float* stash, volatile unsigned* s_done, float (*s_red)[SH::kCW][4],
                                                SelfFeed* sfeed = nullptr) {
   typedef typename IoLoad<TGT>::elem elem;
-  constexpr int LM = (MODE == kModeVjp) ? kVjp : (MODE == kModeVjpL2 ? kVjpL2 : kL2);
+  constexpr int LM = (MODE == kModeVjp) ? kVjp : (MODE == kModeVjpL2 ? kVjpL2 : (MODE == kModeNormFwd ? kRender : kL2));
   float l2w = 0.f, stdv[3] = {1.f, 1.f, 1.f};
+  FixedDiv dstd[3];
+  float amean[3] = {0.f, 0.f, 0.f};
+  if (MODE == kModeNormFwd) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { dstd[c] = make_fixed_div(P.aff_std[c]); amean[c] = P.aff_mean[c]; }
+  }
   if (MODE == kModeVjpL2) {
     l2w = __ldg(P.l2_up) * float(2.0 * P.loss_norm);        // d mse / d out = 2 (out - target) / n_elems, times the upstream scalar
 #pragma unroll
@@ -1024,6 +1063,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
 #else
     texel_prologue(t, pw, tx, ax);
 #endif
+    if constexpr (MODE != kModeNormFwd) {
 #if SV_STASH && !SV_STREAM_ONLY
     {
       float* st = stash + tid;
@@ -1037,8 +1077,22 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       st[24 * SH::kTile] = ax.mx; st[25 * SH::kTile] = ax.my; st[26 * SH::kTile] = ax.mz; st[27 * SH::kTile] = ax.rlen;
     }
 #endif
+    }
     Grads<float> g;
     grads_zero(g);
+    // kModeNormFwd: what norm_l2_kernel does per light after the render — (out - target)^2 into the L2 sum, and
+    // torchvision's Normalize (sub_(mean).div_(std), IEEE division) of the rendered value into the output image
+    auto norm_store = [&](const float o3[3], const float t3[3], int light) {
+      if (valid) {
+        float* __restrict__ dst = P.out + (size_t(light) * 3) * P.stride + p;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float diff = o3[c] - t3[c];
+          g.loss = __fmaf_rn(diff, diff, g.loss);
+          dst[c * P.stride] = div_rn(o3[c] - amean[c], dstd[c]);
+        }
+      }
+    };
 
     // ---- lights, SH::kChunk per ring slot ----
     for (int i0 = 0; i0 < N; i0 += SH::kChunk) {
@@ -1101,6 +1155,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         for (int j = 0; j < SH::kChunk; ++j) {
           float o3[3];
           shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+          if constexpr (MODE == kModeNormFwd) norm_store(o3, in[j], i0 + j);
         }
 #endif
       } else {
@@ -1116,11 +1171,13 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
           if (i0 + j < N) {
             float o3[3];
             shade_light<float, LM, COLOC, WANT_POW>(tx, load_geom<COLOC>(s_geo, i0 + j), in[j], o3, g);
+            if constexpr (MODE == kModeNormFwd) norm_store(o3, in[j], i0 + j);
           }
         }
       }
     }
 
+    if constexpr (MODE != kModeNormFwd) {
     // ---- epilogue ----
 #if SV_STASH && !SV_STREAM_ONLY
     {
@@ -1218,6 +1275,7 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
         *po = gt[k];
         po += ostride;
       }
+    }
     }
     if (valid) {
       loss_acc[0] += grads_loss(g);
@@ -2273,6 +2331,16 @@ static int env_int(const char* name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 
+// What a tile launch does when the ring cannot be set up (too many lights for the shared-memory budget, more CTAs than
+// workspace rows): the one-thread-per-texel kernel — except for the consumer modes, whose LDG kernels live in
+// launch_norm_l2; those get kNoTilePath back and take them.
+constexpr int kNoTilePath = -12345;
+template <int MODE, bool WANT_POW, int TGT>
+static int tile_fallback(const Params& P, cudaStream_t st) {
+  if constexpr (MODE == kModeVjpL2 || MODE == kModeNormFwd) return kNoTilePath;
+  else return launch_texel<MODE, WANT_POW, TGT>(P, st);
+}
+
 template <int MODE, bool WANT_POW, int TGT, typename SH>
 static int launch_tile_shape(Params P, cudaStream_t st) {
   const bool trace = env_int("SVBRDF_B200_TRACE", 0) != 0;
@@ -2289,10 +2357,10 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   const int need = chunks_per_tile<MODE>(P.n_lights, SH::kChunk);
   if (slots > 2 * need) slots = 2 * need;                               // two whole tiles in flight is plenty
   if (slots > 64) slots = 64;
-  if (slots < 2) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (slots < 2) return tile_fallback<MODE, WANT_POW, TGT>(P, st);
   P.slots = slots;
   const size_t smem = size_t(slots) * SH::kSlotBytes + size_t(slots) * 16 + geo + stash_bytes + 16;
-  if (smem + static_smem > size_t(d.smem_optin)) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (smem + static_smem > size_t(d.smem_optin)) return tile_fallback<MODE, WANT_POW, TGT>(P, st);
   auto kern = tile_kernel<MODE, WANT_POW, TGT, SH>;
   static int smem_set[64] = {0};
   if (int e = set_smem_once(reinterpret_cast<const void*>(kern), d.index, smem, smem_set)) return e;
@@ -2320,7 +2388,7 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
     if (grid > 1 && (P.span + SH::kTile - 1) / SH::kTile < tiles_per_cta) tiles_per_cta = (P.span + SH::kTile - 1) / SH::kTile;
   }
   P.counters = reinterpret_cast<unsigned int*>(P.partials + partial_rows(P.texels) * 4);
-  if (grid > kRowsPerEpoch) return launch_texel<MODE, WANT_POW, TGT>(P, st);
+  if (grid > kRowsPerEpoch) return tile_fallback<MODE, WANT_POW, TGT>(P, st);
   if (P.epochs > 1 && tiles_per_cta < 3) {                            // too few tiles per CTA for the lagging publication: one launch per epoch
     Params Q = P;
     for (int e = 0; e < P.epochs; ++e) {
@@ -2558,10 +2626,27 @@ static int launch_norm_l2(Params& P, bool want_pow, int tgt, cudaStream_t st) {
       (reinterpret_cast<uintptr_t>(P.out) & 15) == 0) {
     // one thread per texel with direct LDG ran at 24 % occupancy with 11.6 warps per issued instruction waiting on the
     // long scoreboard (260 us at 1024^2 x 9, profiles/r02_modeb_kernels_1024x9_summary.txt): both streams go through the ring
+    int r = kNoTilePath;
     if (tgt == SVBRDF_TARGET_U8 && tma_ok<SVBRDF_TARGET_U8>(P))
-      return want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_U8>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_U8>(P, st);
-    if (tgt == SVBRDF_TARGET_F32 && tma_ok<SVBRDF_TARGET_F32>(P))
-      return want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_F32>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_F32>(P, st);
+      r = want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_U8>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_U8>(P, st);
+    else if (tgt == SVBRDF_TARGET_F32 && tma_ok<SVBRDF_TARGET_F32>(P))
+      r = want_pow ? launch_vjp_l2_tile<true, SVBRDF_TARGET_F32>(P, st) : launch_vjp_l2_tile<false, SVBRDF_TARGET_F32>(P, st);
+    if (r != kNoTilePath) return r;
+  }
+  if (!BWD && P.io2 && !env_int("SVBRDF_B200_FORCE_LDG", 0) && fixed_div_ok(P.aff_mean, P.aff_std)) {
+    // forward with targets: the targets stream through the ring (kModeNormFwd); one thread per texel with direct LDG and no
+    // prefetch ran at 76.7 us at 1024^2 x 9 (53 % of the HBM roof, profiles/r02_modeb_kernels_1024x9_summary_ring.txt)
+    Params Q = P;
+    Q.io = P.io2;
+    Q.epochs = 1;
+    int r = kNoTilePath;
+    if (tgt == SVBRDF_TARGET_U8 && tma_ok<SVBRDF_TARGET_U8>(Q))
+      r = pick_chunk(Q.n_lights) == 4 ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape4>(Q, st)
+                                      : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape>(Q, st);
+    else if (tgt == SVBRDF_TARGET_F32 && tma_ok<SVBRDF_TARGET_F32>(Q))
+      r = pick_chunk(Q.n_lights) == 4 ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape4>(Q, st)
+                                      : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape>(Q, st);
+    if (r != kNoTilePath) return r;
   }
   const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
   const int blocks = texel_blocks(P);

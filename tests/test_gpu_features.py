@@ -56,6 +56,35 @@ def test_forward_is_eval_then_normalize_then_mse(res, n, coloc):
     assert float(l8) == pytest.approx(float(th.nn.functional.mse_loss(img.double(), t8.double() / 255)), rel=2e-6)
 
 
+@pytest.mark.parametrize("res,n,coloc,u8,chunk", [(256, 9, True, False, 0), (128, 16, True, True, 0), (96, 9, False, False, 4),
+                                                  (500, 4, True, False, 0)])
+def test_forward_on_the_ring_matches_the_ldg_kernel(res, n, coloc, u8, chunk, monkeypatch):
+    """svbrdf_render_norm_l2_fwd streams its targets through the TMA ring (tile_kernel<NormFwd>) and divides by std with the
+    fixed-divisor FMA sequence; the one-thread-per-texel kernel (general IEEE division) must give the same image bit for
+    bit — and both the image torch's own sub/div gives.  Several tiles per CTA, full and partial light chunks (9 lights in
+    4-light slots: 4 + 4 + 1), 3- and 4-light slots, a non-power-of-two resolution."""
+    if chunk:
+        monkeypatch.setenv("SVBRDF_B200_CHUNK", str(chunk))
+    r, t0, target = _setup(res, n, coloc, seed=5)
+    tgt = (target * 255).round().to(th.uint8) if u8 else target
+    with th.no_grad():
+        img = r.eval(t0)
+        norm, l2 = r.eval_normalized(t0, MEAN, STD, tgt)
+        monkeypatch.setenv("SVBRDF_B200_FORCE_LDG", "1")
+        norm_ldg, l2_ldg = r.eval_normalized(t0, MEAN, STD, tgt)
+        monkeypatch.delenv("SVBRDF_B200_FORCE_LDG")
+    mean = th.tensor(MEAN, device=DEV).view(1, 3, 1, 1)
+    std = th.tensor(STD, device=DEV).view(1, 3, 1, 1)
+    assert th.equal(norm, norm_ldg)
+    assert th.equal(norm, (img - mean) / std)
+    assert float(l2) == pytest.approx(float(l2_ldg), rel=2e-6)
+    # awkward divisors: all-ones significand, a power of two, a large and a small one
+    odd_std = [float(np.float32(2.0) - np.float32(2.0 ** -23)), 0.5, 37.25]
+    with th.no_grad():
+        norm2, _ = r.eval_normalized(t0, MEAN, odd_std, tgt)
+    assert th.equal(norm2, (img - mean) / th.tensor(odd_std, device=DEV).view(1, 3, 1, 1))
+
+
 @pytest.mark.parametrize("coloc", [True, False])
 def test_backward_matches_unfused_autograd(coloc):
     """Fused backward vs eval -> normalize -> conv stand-in + mse through torch autograd (the unfused route ends in the
