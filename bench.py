@@ -85,8 +85,13 @@ def config_dict(args, extra=None):
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.005):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        # seconds between NVML polls.  Dense (5 ms) while a region is timed on the DEVICE; the regions timed through the
+        # host API (`e2e`, `e2e_job`) are sampled every 100 ms: every poll takes the driver's global lock and the GIL, and at
+        # 200 polls/s the host-side submission of the 28 MB upload + launch + read-back of one e2e step took 1.02 ms instead
+        # of 0.61 ms (tools/e2e_breakdown.py on the same box type).
+        self.interval = interval
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -119,7 +124,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.interval)
 
     def __enter__(self):
         if self.nv is not None:
@@ -135,7 +140,7 @@ class ClockSampler:
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "poll_s": {"device_timed_legs": 0.005, "host_timed_legs": self.interval}}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -356,6 +361,7 @@ def run_b200_arm(args):
 
     # ---- e2e: per step, upload that step's targets from pinned host memory, run, read the loss back ----
     e2e = e2e_job = None
+    clk.interval = 0.1                                   # host-timed regions: keep the poller out of the submission path
     if not args.no_e2e:
         o = pkg.SvbrdfOptim(dev, r)
         host_targets = [m["target"].cpu().pin_memory() for m in mats[:2]]
