@@ -88,9 +88,10 @@ class ClockSampler:
     def __init__(self, index, interval=0.005):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         # seconds between NVML polls.  Dense (5 ms) while a region is timed on the DEVICE; the regions timed through the
-        # host API (`e2e`, `e2e_job`) are sampled every 100 ms: every poll takes the driver's global lock and the GIL, and at
-        # 200 polls/s the host-side submission of the 28 MB upload + launch + read-back of one e2e step took 1.02 ms instead
-        # of 0.61 ms (tools/e2e_breakdown.py on the same box type).
+        # host API (`e2e`, `e2e_job`) are sampled every 100 ms: every poll takes the driver's global lock and the GIL, which
+        # the submission path of an e2e step (upload, launch, read-back, synchronise) needs too.  (The e2e step itself varies
+        # between boxes of the pool: 0.61-0.67 ms where the pinned upload runs at 53 GB/s, 1.0-1.1 ms where it reaches 28 GB/s;
+        # tools/e2e_breakdown.py splits a step into upload / kernel / read-back.)
         self.interval = interval
         self._stop = threading.Event()
         self._thr = None
@@ -380,7 +381,7 @@ def run_b200_arm(args):
             host_loss.copy_(loss_dev, non_blocking=True)                            # D2H of the step's result
             th.cuda.current_stream().synchronize()
 
-        for i in range(2):
+        for i in range(max(W, 3)):
             e2e_step(i)
         ms_e = timed(e2e_step, e2e_steps)
         e2e_f32 = {"value": samples_per_step * world * e2e_steps / (ms_e * 1e-3), "unit": UNIT,
@@ -400,7 +401,7 @@ def run_b200_arm(args):
             host_loss.copy_(loss_dev, non_blocking=True)
             th.cuda.current_stream().synchronize()
 
-        for i in range(2):
+        for i in range(max(W, 3)):
             e2e_step_u8(i)
         ms_u8 = timed(e2e_step_u8, e2e_steps)
         e2e = {"value": samples_per_step * world * e2e_steps / (ms_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": stage_u8.numel(),
