@@ -913,17 +913,15 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
                                                SelfFeed* sfeed = nullptr) {
   typedef typename IoLoad<TGT>::elem elem;
   constexpr int LM = (MODE == kModeVjp) ? kVjp : (MODE == kModeVjpL2 ? kVjpL2 : (MODE == kModeNormFwd ? kRender : kL2));
-  float l2w = 0.f, stdv[3] = {1.f, 1.f, 1.f};
+  float l2w = 0.f;
   FixedDiv dstd[3];
   float amean[3] = {0.f, 0.f, 0.f};
-  if (MODE == kModeNormFwd) {
+  if (MODE == kModeNormFwd || MODE == kModeVjpL2) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { dstd[c] = make_fixed_div(P.aff_std[c]); amean[c] = P.aff_mean[c]; }
+    for (int c = 0; c < 3; ++c) { dstd[c] = make_fixed_div(P.aff_std[c]); amean[c] = MODE == kModeNormFwd ? P.aff_mean[c] : 0.f; }
   }
   if (MODE == kModeVjpL2) {
     l2w = __ldg(P.l2_up) * float(2.0 * P.loss_norm);        // d mse / d out = 2 (out - target) / n_elems, times the upstream scalar
-#pragma unroll
-    for (int c = 0; c < 3; ++c) stdv[c] = P.aff_std[c];
   }
   const int tid = threadIdx.x, lane = tid & 31;
   const int N = P.n_lights, S = P.slots;
@@ -1100,13 +1098,15 @@ __device__ __forceinline__ void tile_consumer(const Params& P, const float4* __r
       float tg[MODE == kModeVjpL2 ? SH::kChunk : 1][3];
       if constexpr (MODE == kModeVjpL2) {
         // first slot of the chunk: the upstream gradient of the normalised image, d((x - mean)/std)/dx = 1/std applied here
-        // (IEEE division like the unfused torch route); lights past N were not loaded: their values are never used
+        // (correctly rounded like the unfused torch route's division: the fixed-divisor FMA sequence, see FixedDiv — it can
+        // differ from IEEE division by an ulp only where the quotient or the residual is subnormal, |grad| < ~1e-30);
+        // lights past N were not loaded: their values are never used
         wait_full();
         const float* sg = reinterpret_cast<const float*>(ring + size_t(slot) * SH::kSlotBytes);
 #pragma unroll
         for (int j = 0; j < SH::kChunk; ++j) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? __fdiv_rn(sg[(j * 3 + c) * kPS + tixL], stdv[c]) : 0.f;
+          for (int c = 0; c < 3; ++c) in[j][c] = (i0 + j < N) ? div_rn(sg[(j * 3 + c) * kPS + tixL], dstd[c]) : 0.f;
         }
         release(slot);
         advance();
@@ -2622,8 +2622,9 @@ static int launch_vjp_l2_tile(const Params& P, cudaStream_t st) {
 
 template <bool BWD>
 static int launch_norm_l2(Params& P, bool want_pow, int tgt, cudaStream_t st) {
+  const float no_mean[3] = {0.f, 0.f, 0.f};
   if (BWD && P.io2 && P.l2_up && !env_int("SVBRDF_B200_FORCE_LDG", 0) && (reinterpret_cast<uintptr_t>(P.io2) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(P.out) & 15) == 0) {
+      (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 && fixed_div_ok(no_mean, P.aff_std)) {
     // one thread per texel with direct LDG ran at 24 % occupancy with 11.6 warps per issued instruction waiting on the
     // long scoreboard (260 us at 1024^2 x 9, profiles/r02_modeb_kernels_1024x9_summary.txt): both streams go through the ring
     int r = kNoTilePath;
