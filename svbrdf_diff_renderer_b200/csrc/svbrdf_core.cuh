@@ -944,6 +944,35 @@ template <typename T>
 SV_HD T pow_grad(T acc, T pw) { return pw != T(0) ? acc / pw : T(0); }   // scalar only (finalisation)
 
 // ---------------------------------------------------------------------------------------------
+// x / b with IEEE rounding for a divisor that is fixed for the whole launch (the per-channel std of Normalize): the
+// correctly rounded reciprocal r = RN(1/b) is formed once, then q0 = RN(x r), rem = x - q0 b (exact in an FMA),
+// q = RN(q0 + rem r) is the correctly rounded quotient (Markstein) — three FMA-pipe instructions instead of the ~10 plus a
+// MUFU.RCP of the general division.  tests/test_host_logic.py runs this very code (host build) against IEEE division on
+// millions of (x, b) pairs incl. all-ones significands (the one difference: a -0.0 numerator gives +0.0);
+// tests/test_gpu_features.py compares the normalised image with torch's.  Launches whose divisors lie outside [1e-30, 1e30] (reciprocal or quotient could leave the normal range) keep
+// the general division (norm_l2_kernel).
+// ---------------------------------------------------------------------------------------------
+struct FixedDiv {
+  float b, r;
+};
+SV_HD FixedDiv make_fixed_div(float b) {
+  FixedDiv d;
+  d.b = b;
+#if defined(__CUDA_ARCH__)
+  d.r = __fdiv_rn(1.f, b);
+#else
+  d.r = 1.0f / b;
+#endif
+  return d;
+}
+SV_HD float div_rn(float x, const FixedDiv& d) {
+  typedef Fm<float> S;
+  const float q0 = S::mul(x, d.r);
+  const float rem = S::fma(-q0, d.b, x);
+  return S::fma(rem, d.r, q0);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adam (torch/optim/adam.py:531-547, single-tensor path, amsgrad off, weight decay 0).
 //   m <- m + (g - m)(1 - b1);  v <- v*b2 + (1 - b2) g^2;
 //   p <- p - step_size * m / (sqrt(v)/sqrt(bc2) + eps),  step_size = lr/bc1

@@ -606,27 +606,7 @@ __global__ void __launch_bounds__(kThreads) texel_kernel(const Params P) {
 // normalised image, adds the L2 term's gradient from the target and chains to the textures (instead of 4 image-sized
 // passes + the render VJP).  One thread per texel, direct LDG/STG.
 // ---------------------------------------------------------------------------------------------
-// x / b with IEEE rounding for a divisor that is fixed for the whole launch (the per-channel std of Normalize): the
-// correctly rounded reciprocal r = RN(1/b) is formed once, then q0 = RN(x r), rem = x - q0 b (exact in an FMA),
-// q = RN(q0 + rem r) is the correctly rounded quotient (Markstein) — three FMA-pipe instructions instead of the ~10 plus a
-// MUFU.RCP of the general division.  Checked against IEEE division with exact rational arithmetic for 196 000 (x, b)
-// pairs incl. all-ones significands; tests/test_gpu_features.py compares the normalised image with torch bit for bit.
-// Launches whose divisors lie outside [1e-30, 1e30] (reciprocal or quotient could leave the normal range) keep the
-// general division (norm_l2_kernel).
-struct FixedDiv {
-  float b, r;
-};
-__device__ __forceinline__ FixedDiv make_fixed_div(float b) {
-  FixedDiv d;
-  d.b = b;
-  d.r = __fdiv_rn(1.f, b);
-  return d;
-}
-__device__ __forceinline__ float div_rn(float x, const FixedDiv& d) {
-  const float q0 = __fmul_rn(x, d.r);
-  const float rem = __fmaf_rn(-q0, d.b, x);
-  return __fmaf_rn(rem, d.r, q0);
-}
+// FixedDiv / make_fixed_div / div_rn (x / b with IEEE rounding for a divisor fixed per launch) live in svbrdf_core.cuh.
 // the launcher's side of the contract: every divisor and every mean inside the range where neither r nor q can leave the
 // normal range for a rendered value in [0, 1]
 static bool fixed_div_ok(const float* mean, const float* std_) {

@@ -180,6 +180,16 @@ void dispatch(int coloc, int mode, T* tex, const T* cam, const T* light, const T
 
 extern "C" {
 
+// x[i] / b through the kernels' fixed-divisor sequence (svbrdf_core.cuh div_rn) and through the IEEE division
+void emu_fixed_div(int n, const float* x, float b, float* by_sequence, float* by_division) {
+  const FixedDiv d = make_fixed_div(b);
+  for (int i = 0; i < n; ++i) {
+    by_sequence[i] = div_rn(x[i], d);
+    volatile float q = x[i] / b;
+    by_division[i] = q;
+  }
+}
+
 // texel centres of one row/column: the reference's division (texel_position) and the kernels' corrected-reciprocal form
 void emu_positions(int res, float size, float* by_division, float* by_reciprocal) {
   const float inv = 1.0f / float(res);

@@ -165,3 +165,31 @@ def test_texel_positions_are_bit_identical_to_the_reference_division():
         if res in (40, 48, 1100, 4096):          # and the division form is torch's: the reference's own expression
             t = ((th.arange(res, dtype=th.float32) + 0.5) / res - 0.5) * 6.848
             assert np.array_equal(a[0::2], t.numpy()) and np.array_equal(a[1::2], -t.numpy())
+
+
+def test_fixed_divisor_division_is_ieee_division():
+    """svbrdf_core.cuh div_rn — q0 = RN(x r), rem = fma(-q0, b, x), q = fma(rem, r, q0) with r = RN(1/b) — is what the consumer
+    kernels use for Normalize's division by std.  The host build of that code must agree with the IEEE division bit for bit:
+    the torchvision constants, awkward divisors (all-ones significand, powers of two, just above/below them), random ones;
+    numerators over the range a normalised image or its gradient can take."""
+    import ctypes
+
+    from tests import hostemu
+    L = hostemu.lib()
+    rng = np.random.default_rng(11)
+    ones = np.float32(2.0) - np.float32(2.0 ** -23)
+    divisors = [0.229, 0.224, 0.225, 0.255, 0.5, 1.0, 2.0, float(ones), float(ones) / 4, float(np.nextafter(np.float32(1), np.float32(2))),
+                float(np.nextafter(np.float32(1), np.float32(0))), 3.0, 1e-3, 37.25, 1e4] + list(rng.uniform(0.01, 10.0, 25))
+    xs = np.concatenate([
+        rng.uniform(-1.0, 1.0, 400_000),
+        rng.uniform(0.0, 1.0, 200_000) - 0.485,                       # a rendered value minus a mean
+        rng.standard_normal(200_000) * 10.0 ** rng.uniform(-12, 2, 200_000),   # gradients over 14 decades
+        [0.0, -0.0, 1.0, -1.0, 1e-20, -1e-20, 1e20],
+    ]).astype(np.float32)
+    a, b = np.empty_like(xs), np.empty_like(xs)
+    for d in divisors:
+        L.emu_fixed_div(xs.size, xs.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(d), a.ctypes.data_as(ctypes.c_void_p),
+                        b.ctypes.data_as(ctypes.c_void_p))
+        nz = xs != 0                                                   # a -0.0 numerator comes out as +0.0 (equal as a number)
+        assert np.array_equal(a.view(np.uint32)[nz], b.view(np.uint32)[nz]), d
+        assert np.array_equal(a, b) and np.array_equal(b, xs / np.float32(d))
