@@ -2328,7 +2328,7 @@ static int launch_tile_shape(Params P, cudaStream_t st) {
   if (int e = device_info(&d)) return e;
   const int ctas_per_sm = env_int("SVBRDF_B200_CTAS_PER_SM", 1);
   const size_t geo = size_t(P.n_lights) * 2 * sizeof(float4);
-  const size_t stash_bytes = SV_STASH ? size_t(kStashFloats) * SH::kTile * 4 : 0;
+  const size_t stash_bytes = (SV_STASH && MODE != kModeNormFwd) ? size_t(kStashFloats) * SH::kTile * 4 : 0;   // the forward-only mode parks nothing
   const size_t fixed = geo + stash_bytes + 64 + 2 * 8 * 64;            // barriers (<= 64 slots) + padding
   const size_t static_smem = 1024;                                     // s_done + s_red (static __shared__)
   const size_t budget = size_t(d.smem_optin + 1024) / ctas_per_sm - 1024 - static_smem;
@@ -2621,12 +2621,15 @@ static int launch_norm_l2(Params& P, bool want_pow, int tgt, cudaStream_t st) {
     Q.io = P.io2;
     Q.epochs = 1;
     int r = kNoTilePath;
+    // (23 + 1 warps at 80 registers — the forward-only body fits — were measured too: 57.6 vs 58.5 us, issue slots 75 vs 71 %;
+    // not worth a second shape)
+    const bool four = pick_chunk(Q.n_lights) == 4;
     if (tgt == SVBRDF_TARGET_U8 && tma_ok<SVBRDF_TARGET_U8>(Q))
-      r = pick_chunk(Q.n_lights) == 4 ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape4>(Q, st)
-                                      : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape>(Q, st);
+      r = four ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape4>(Q, st)
+               : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_U8, ScalarShape>(Q, st);
     else if (tgt == SVBRDF_TARGET_F32 && tma_ok<SVBRDF_TARGET_F32>(Q))
-      r = pick_chunk(Q.n_lights) == 4 ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape4>(Q, st)
-                                      : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape>(Q, st);
+      r = four ? launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape4>(Q, st)
+               : launch_tile_shape<kModeNormFwd, false, SVBRDF_TARGET_F32, ScalarShape>(Q, st);
     if (r != kNoTilePath) return r;
   }
   const size_t smem = size_t(P.n_lights) * 2 * sizeof(float4);
