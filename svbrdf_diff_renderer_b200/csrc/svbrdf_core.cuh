@@ -545,6 +545,12 @@ SV_HD void channels(const T fp[3], const T Fp[3], T w, T Q, const T io[3], T out
 #ifndef SV_RCP_MERGE
 #define SV_RCP_MERGE 0
 #endif
+// SV_ST_FROM_SF: the per-light accumulation of sum T (co-located body) is replaced by sum_c Fp_c sF_c in the epilogue: one
+// instruction per light less (104 -> 103), 70.9 -> 70.2 us at 1024^2 x 9 but 1146 -> 1157 us at 2048^2 x 64 and 4492-4510 ->
+// 4530 us at 4096^2 x 64 (the schedule ptxas finds matters more than the count): off
+#ifndef SV_ST_FROM_SF
+#define SV_ST_FROM_SF 0
+#endif
 #ifndef SV_NV_FOLD
 #define SV_NV_FOLD 0
 #endif
@@ -720,7 +726,9 @@ SV_HD void shade_light_coloc(const Texel<T>& tx, const LightGeom<T>& lg, const T
 
   const T gQ = w * B;                                         // dL/dQ = sum_c dL/dfp_c Fp_c
   const T Tq = gQ * Q;
+#if !SV_ST_FROM_SF
   g.sT += Tq;
+#endif
 #if SV_RCP_MERGE
   const T TR = Tq * R;
   const T E = TR * (g2 * q4 * pden);                          // T pden / Dd
@@ -918,7 +926,13 @@ SV_HD void texel_epilogue(const Texel<T>& tx, const TexelAux<T>& ax, const T pw[
     // to zero (-> inf, and a -inf roughness gradient), and at a2 = 0 the reference's dD/da2 = 1/Dd is finite but rough = 0
     // zeroes the channel's chain factor.  Dropping it is exact to fp32: Q/a2 = c^2/(Dd gv^2 q) <= 1e12, and the chain
     // factor of the roughness channel, 4 rough^3 dpow = 4 a2^(3/4) dpow, is < 2e-22 there.
-    ga2 = F::fma(g.a2, T(-2), F::sel(F::ge(T(1e-30), tx.a2), T(0), g.sT * F::rcp(tx.a2)));
+#if SV_ST_FROM_SF
+    // sum_l T_l = sum_l w_l Q_l sum_c gI_c Fp_c = sum_c Fp_c sF_c: the accumulators the Fresnel-albedo gradient needs anyway
+    const T sT = F::fma(tx.Fp[0], g.sF[0], F::fma(tx.Fp[1], g.sF[1], tx.Fp[2] * g.sF[2]));
+#else
+    const T sT = g.sT;
+#endif
+    ga2 = F::fma(g.a2, T(-2), F::sel(F::ge(T(1e-30), tx.a2), T(0), sT * F::rcp(tx.a2)));
     gk = g.k * T(-2);
   }
 #endif
